@@ -1,0 +1,162 @@
+/*
+ * smk.h -- C ABI of the B200-native SimpleMOC-kernel segment-attenuation path.
+ *
+ * The reference has no plugin/FFI layer: its seam is the plain C call
+ *     void run_kernel(Input *I, Source *S, Table *table);
+ * (/root/reference/src/cpu/SimpleMOC-kernel_header.h:81, called once from
+ * /root/reference/src/cpu/main.c:46, and its CUDA twin launched from
+ * /root/reference/src/cuda/main.cu:90).  This header is what a C host driver
+ * (ours: simplemoc-kernel_b200/host/smk_main.c; the reference's main.c with the
+ * three-line patch shown in INTEGRATION.md) binds instead.  Plain pointers and
+ * sizes only; no CUDA or torch types appear in any signature.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative SMK_E* code on failure,
+ *     and never calls exit(); smk_last_error() returns the message of the last
+ *     failure on the calling thread (the reference prints "Error at file:line"
+ *     and returns EXIT_FAILURE, /root/reference/src/cuda/SimpleMOC-kernel_header.h:24-26).
+ *   - host arrays use the reference's unpadded layouts (init.c:35-54):
+ *         fine_source[R][F][G], fine_flux[R][F][G], sigT[R][G]   (float)
+ *     with R = source_3D_regions, F = fine_axial_intervals, G = egroups.
+ *   - device arrays are padded to G_pad groups per row (smk_padded_groups()).
+ *   - a "track" is seg_per_track consecutive segments of the deterministic
+ *     stream that share one carried angular flux.
+ */
+#ifndef SMK_H
+#define SMK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMK_ABI_VERSION 1
+
+/* error codes */
+#define SMK_OK          0
+#define SMK_EINVAL     -1   /* bad argument / unsupported configuration        */
+#define SMK_ECUDA      -2   /* a CUDA runtime call failed                      */
+#define SMK_ENOMEM     -3   /* host or device allocation failed                */
+#define SMK_ESTATE     -4   /* call made in the wrong state (e.g. no upload)   */
+
+/* how 1 - exp(-tau) is evaluated (kernel.c:216-223) */
+#define SMK_EXP_POLY    0   /* FMA-pipe polynomial, correctly rounded where the
+                               reference formula is ill-conditioned (default)  */
+#define SMK_EXP_MUFU    1   /* MUFU.EX2 (ex2.approx.ftz), 2 ulp                 */
+#define SMK_EXP_GLIBC   2   /* double-precision replica of glibc 2.39 expf      */
+#define SMK_EXP_TABLE   3   /* the reference's interpolation table
+                               (init.c:81-117, kernel.c:337-361; TABLE build)  */
+
+/* arithmetic of the attenuation formulae */
+#define SMK_MATH_FAST   0   /* FMA contraction, one MUFU.RCP instead of 5 divides */
+#define SMK_MATH_STRICT 1   /* the reference's operation order, IEEE div, no FMA:
+                               per-intersection results are bit-identical to a
+                               -O2 -ffp-contract=off build of kernel.c          */
+
+/*
+ * Problem description.  Fields 1-5 are the reference's Input
+ * (/root/reference/src/cpu/SimpleMOC-kernel_header.h:24-33) plus the CUDA
+ * variant's seg_per_thread (/root/reference/src/cuda/SimpleMOC-kernel_header.h:39,
+ * the -p option, io.cu:141-147); the rest configure the changed subsystems.
+ */
+typedef struct smk_params {
+    int32_t  source_3D_regions;     /* R  (main.c:18-19)                        */
+    int32_t  fine_axial_intervals;  /* F  (init.c:10), must be >= 2             */
+    int32_t  egroups;               /* G  (-e)                                  */
+    int32_t  seg_per_track;         /* -p, default 100 (init.cu:41)             */
+    int64_t  segments;              /* N  (-s)                                  */
+    uint64_t seed;                  /* key of the counter-based stream          */
+    int32_t  exp_mode;              /* SMK_EXP_*                                */
+    int32_t  math_mode;             /* SMK_MATH_*                               */
+    int32_t  device;                /* CUDA device ordinal (-d, io.cu:148-158)  */
+    int32_t  flags;                 /* SMK_FLAG_*                               */
+} smk_params;
+
+#define SMK_FLAG_KEEP_PSI  1        /* keep each track's outgoing psi (tests)   */
+
+typedef struct smk_ctx smk_ctx;     /* opaque: device buffers, stream, events   */
+
+/* ---- library ---------------------------------------------------------- */
+int          smk_abi_version(void);
+const char  *smk_last_error(void);
+int          smk_device_count(void);
+/* name of device `device` copied into buf (the reference prints it, io.cu:87) */
+int          smk_device_name(int device, char *buf, size_t buflen);
+/* G_pad for G groups: row stride, in floats, of every device array */
+int          smk_padded_groups(int egroups);
+int64_t      smk_num_tracks(int64_t segments, int seg_per_track);
+
+/* ---- context ---------------------------------------------------------- */
+/* allocates device buffers for p on p->device; replaces initialize_device_sources
+ * (/root/reference/src/cuda/init.cu:105-127) */
+int   smk_create(const smk_params *p, smk_ctx **out);
+void  smk_destroy(smk_ctx *ctx);
+/* run on a caller-owned cudaStream_t (passed as void*) instead of the context's */
+int   smk_set_stream(smk_ctx *ctx, void *cuda_stream);
+
+/* ---- data ------------------------------------------------------------- */
+/* host (unpadded, pageable or pinned) -> device (padded); tallies are zeroed.
+ * fine_flux may be NULL (initial scalar flux = 0). */
+int   smk_upload(smk_ctx *ctx, const float *fine_source, const float *fine_flux,
+                 const float *sigT);
+/* device-side deterministic fill, bit-identical to the host stream fill that
+ * replaces init.c:64-75; sigt_floor = 0 for U[0,1) */
+int   smk_fill_device(smk_ctx *ctx, float sigt_floor);
+/* zero the tally deltas (start of a new sweep) */
+int   smk_reset_tallies(smk_ctx *ctx);
+/* fine_flux_out[R][F][G] = initial flux + tallies accumulated since the last
+ * reset (kernel.c:274-277 applied to every replayed segment) */
+int   smk_download_flux(smk_ctx *ctx, float *fine_flux_out);
+/* outgoing psi of tracks [track_begin, track_end) of the LAST run:
+ * psi_out[(t - track_begin) * G + g]; needs SMK_FLAG_KEEP_PSI */
+int   smk_download_psi(smk_ctx *ctx, float *psi_out);
+/* sum over replayed segments s of (QSR_id*F + FAI_id + 1) * ((s & 0xFFFF) + 1)
+ * mod 2^64, accumulated since the last reset: the indexing fingerprint */
+int   smk_download_checksum(smk_ctx *ctx, uint64_t *checksum);
+
+/* ---- the hot path ------------------------------------------------------ */
+/* attenuate tracks [track_begin, track_end) (run_kernel's segment loop,
+ * kernel.c:43-55).  Synchronous; *kernel_seconds (may be NULL) receives the
+ * CUDA-event time of the kernel alone, as main.cu:89-96 measures it. */
+int   smk_run(smk_ctx *ctx, int64_t track_begin, int64_t track_end,
+              double *kernel_seconds);
+/* same, enqueue only (no synchronisation, no timing) */
+int   smk_run_async(smk_ctx *ctx, int64_t track_begin, int64_t track_end);
+int   smk_synchronize(smk_ctx *ctx);
+/* number of kernel launches issued through ctx since creation */
+int64_t smk_launch_count(const smk_ctx *ctx);
+
+/*
+ * Drop-in for run_kernel(I, S, table) with HOST slabs: upload, attenuate all
+ * tracks, download.  fine_flux is updated in place like the reference does
+ * (kernel.c:276).  kernel_seconds / total_seconds may be NULL.
+ */
+int   smk_run_host(const smk_params *p, const float *fine_source,
+                   float *fine_flux, const float *sigT,
+                   double *kernel_seconds, double *total_seconds);
+
+/* ---- plumbing for callers that own device memory (torch, NCCL) --------- */
+/* raw device pointers of the context's padded arrays (void* = float*) */
+void *smk_device_tally(smk_ctx *ctx);      /* [R][F][G_pad], the all-reduce operand */
+void *smk_device_flux0(smk_ctx *ctx);      /* [R][F][G_pad] initial flux            */
+void *smk_device_source(smk_ctx *ctx);     /* [R][F][G_pad]                         */
+void *smk_device_sigT(smk_ctx *ctx);       /* [R][G_pad]                            */
+int64_t smk_padded_elems(const smk_ctx *ctx); /* R*F*G_pad                          */
+/* pinned host memory for end-to-end runs */
+void *smk_alloc_host(size_t bytes);
+void  smk_free_host(void *p);
+
+/* ---- diagnostics ------------------------------------------------------- */
+/* d_out[i] = exp(-tau[i]) as evaluated by exp_mode (host arrays, n elements);
+ * used to sweep the exponential against libm */
+int   smk_debug_exp(int exp_mode, const float *tau, float *out, int64_t n, int device);
+/* (QSR_id, FAI_id) of segments [seg_begin, seg_begin+n) as the kernel draws them */
+int   smk_debug_segment_ids(const smk_params *p, int64_t seg_begin, int64_t n,
+                            int32_t *qsr_out, int32_t *fai_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMK_H */

@@ -36,6 +36,8 @@ def build(ref: bool = True) -> None:
 
 
 def n_tracks(segments: int, seg_per_track: int) -> int:
+    if seg_per_track < 1:
+        raise ValueError("seg_per_track must be >= 1")
     return (segments + seg_per_track - 1) // seg_per_track
 
 

@@ -296,7 +296,7 @@ void smk_oracle_attenuate_segment(int groups, int fai_count, int FAI_id,
  * psi_final, if non-NULL, receives the outgoing psi of each track in
  * [track_begin, track_end): psi_final[(t - track_begin)*groups + g].
  * id_checksum, if non-NULL, receives sum over segments of
- * (QSR_id*fai + FAI_id + 1) * (seg % 65521 + 1) mod 2^64 (indexing fingerprint). */
+ * (QSR_id*fai + FAI_id + 1) * ((seg & 0xFFFF) + 1) mod 2^64 (indexing fingerprint). */
 int smk_oracle_run(int regions, int fai, int groups, int64_t segments,
                    int seg_per_track, uint64_t seed,
                    const float *fine_source, float *fine_flux, const float *sigT,
@@ -349,7 +349,7 @@ int smk_oracle_run(int regions, int fai, int groups, int64_t segments,
                 int32_t QSR_id, FAI_id;
                 smk_oracle_segment_ids(seed, s, 1, regions, fai, &QSR_id, &FAI_id);
                 checksum += ((uint64_t)QSR_id * (uint64_t)fai + (uint64_t)FAI_id + 1u)
-                            * ((uint64_t)(s % 65521) + 1u);
+                            * ((uint64_t)(s & 0xFFFF) + 1u);
 
                 attenuate_one_segment(groups, fai, FAI_id,
                                       fine_source + (int64_t)QSR_id * fai * groups,

@@ -1,0 +1,307 @@
+"""B200-native SimpleMOC-kernel segment-attenuation path: ctypes binding of libsmk.so.
+
+This package is the Python-side mirror of the C ABI in include/smk.h (the product's
+host driver is the plain-C program host/smk_main.c; this module exists for tests,
+bench.py and torch.distributed plumbing).  All compute happens in the hand-written
+sm_100a kernels of csrc/; there is NO CPU fallback: if lib/libsmk.so is missing or
+does not load, importing this package raises.
+
+Reference interface mirrored here
+  Input / set_default_input   /root/reference/src/cpu/SimpleMOC-kernel_header.h:24-42,
+                              /root/reference/src/cpu/init.c:4-24 (+ streams /
+                              seg_per_thread of /root/reference/src/cuda/init.cu:30-44)
+  run_kernel(I, S)            /root/reference/src/cpu/kernel.c:3-73
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libsmk.so")
+
+EXP_POLY, EXP_MUFU, EXP_GLIBC, EXP_TABLE = 0, 1, 2, 3
+MATH_FAST, MATH_STRICT = 0, 1
+FLAG_KEEP_PSI = 1
+
+EXP_MODES = {"poly": EXP_POLY, "mufu": EXP_MUFU, "glibc": EXP_GLIBC, "table": EXP_TABLE}
+MATH_MODES = {"fast": MATH_FAST, "strict": MATH_STRICT}
+
+
+class SmkError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """struct smk_params (include/smk.h)."""
+    _fields_ = [
+        ("source_3D_regions", C.c_int32),
+        ("fine_axial_intervals", C.c_int32),
+        ("egroups", C.c_int32),
+        ("seg_per_track", C.c_int32),
+        ("segments", C.c_int64),
+        ("seed", C.c_uint64),
+        ("exp_mode", C.c_int32),
+        ("math_mode", C.c_int32),
+        ("device", C.c_int32),
+        ("flags", C.c_int32),
+    ]
+
+
+def build(verbose: bool = False) -> str:
+    """Compile lib/libsmk.so and bin/SimpleMOC-kernel for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", HERE, "all"] + ([] if verbose else ["-s"])
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+
+# every symbol include/smk.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = (
+    "smk_abi_version", "smk_last_error", "smk_device_count", "smk_device_name",
+    "smk_padded_groups", "smk_num_tracks", "smk_create", "smk_destroy", "smk_set_stream",
+    "smk_upload", "smk_fill_device", "smk_reset_tallies", "smk_download_flux",
+    "smk_download_psi", "smk_download_checksum", "smk_run", "smk_run_async",
+    "smk_synchronize", "smk_launch_count", "smk_run_host", "smk_device_tally",
+    "smk_device_flux0", "smk_device_source", "smk_device_sigT", "smk_padded_elems",
+    "smk_alloc_host", "smk_free_host", "smk_debug_exp", "smk_debug_segment_ids",
+)
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension is the product and there is no CPU fallback. "
+            "Build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`make -C simplemoc-kernel_b200`.")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    L.smk_abi_version.restype = i32
+    L.smk_last_error.restype = C.c_char_p
+    L.smk_device_count.restype = i32
+    L.smk_device_name.argtypes = [i32, C.c_char_p, C.c_size_t]
+    L.smk_padded_groups.argtypes = [i32]
+    L.smk_num_tracks.argtypes = [i64, i32]
+    L.smk_num_tracks.restype = i64
+    L.smk_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    L.smk_destroy.argtypes = [vp]
+    L.smk_destroy.restype = None
+    L.smk_set_stream.argtypes = [vp, vp]
+    L.smk_upload.argtypes = [vp, vp, vp, vp]
+    L.smk_fill_device.argtypes = [vp, C.c_float]
+    L.smk_reset_tallies.argtypes = [vp]
+    L.smk_download_flux.argtypes = [vp, vp]
+    L.smk_download_psi.argtypes = [vp, vp]
+    L.smk_download_checksum.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.smk_run.argtypes = [vp, i64, i64, C.POINTER(C.c_double)]
+    L.smk_run_async.argtypes = [vp, i64, i64]
+    L.smk_synchronize.argtypes = [vp]
+    L.smk_launch_count.argtypes = [vp]
+    L.smk_launch_count.restype = i64
+    L.smk_run_host.argtypes = [C.POINTER(Params), vp, vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    for name in ("smk_device_tally", "smk_device_flux0", "smk_device_source", "smk_device_sigT"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = vp
+    L.smk_padded_elems.argtypes = [vp]
+    L.smk_padded_elems.restype = i64
+    L.smk_alloc_host.argtypes = [C.c_size_t]
+    L.smk_alloc_host.restype = vp
+    L.smk_free_host.argtypes = [vp]
+    L.smk_free_host.restype = None
+    L.smk_debug_exp.argtypes = [i32, _f32p, _f32p, i64, i32]
+    L.smk_debug_segment_ids.argtypes = [C.POINTER(Params), i64, i64, _i32p, _i32p]
+    return L
+
+
+lib = _load()
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise SmkError(f"libsmk error {rc}: {lib.smk_last_error().decode()}")
+
+
+# ---------------------------------------------------------------------------
+# the reference's Input (header.h:24-42) with the CUDA variant's extra fields
+# ---------------------------------------------------------------------------
+@dataclass
+class Input:
+    source_2D_regions: int = 5000        # init.c:8
+    coarse_axial_intervals: int = 27     # init.c:9
+    fine_axial_intervals: int = 5        # init.c:10
+    decomp_assemblies_ax: int = 20       # init.c:11
+    segments: int = 50_000_000           # init.c:12
+    egroups: int = 128                   # init.c:13
+    nthreads: int = 0                    # -t: CPU threads of the verification replay only
+    seg_per_thread: int = 100            # -p (cuda/init.cu:41): segments per track
+    source_3D_regions: int = 0           # derived, main.c:18-19
+    # changed subsystems (north star): stream seed, exponential and arithmetic modes, device
+    seed: int = 42
+    exp_mode: str = "poly"
+    math_mode: str = "fast"
+    device: int = 0
+
+    def finalize(self) -> "Input":
+        """main.c:18-19: source_3D_regions = ceil(2D * coarse / decomp)."""
+        self.source_3D_regions = int(math.ceil(
+            float(self.source_2D_regions) * self.coarse_axial_intervals / self.decomp_assemblies_ax))
+        return self
+
+    @property
+    def n_tracks(self) -> int:
+        return (self.segments + self.seg_per_thread - 1) // self.seg_per_thread
+
+    def params(self, flags: int = 0) -> Params:
+        if self.source_3D_regions == 0:
+            self.finalize()
+        return Params(self.source_3D_regions, self.fine_axial_intervals, self.egroups,
+                      self.seg_per_thread, self.segments, self.seed, EXP_MODES[self.exp_mode],
+                      MATH_MODES[self.math_mode], self.device, flags)
+
+
+def set_default_input() -> Input:
+    """init.c:4-24 / cuda init.cu:30-44."""
+    return Input().finalize()
+
+
+class Context:
+    """Device-resident problem: padded source / sigT / flux arrays + tally deltas."""
+
+    def __init__(self, I: Input, keep_psi: bool = False):
+        self.I = I
+        self.p = I.params(FLAG_KEEP_PSI if keep_psi else 0)
+        self._h = C.c_void_p()
+        _check(lib.smk_create(C.byref(self.p), C.byref(self._h)))
+        self.R, self.F, self.G = self.p.source_3D_regions, self.p.fine_axial_intervals, self.p.egroups
+        self.G_pad = lib.smk_padded_groups(self.G)
+        self.n_tracks = lib.smk_num_tracks(self.p.segments, self.p.seg_per_track)
+
+    def close(self):
+        if self._h:
+            lib.smk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _ptr(a):
+        """host pointer of a numpy array / torch CPU tensor / raw int address (or None)."""
+        if a is None:
+            return None
+        if isinstance(a, int):
+            return a
+        if isinstance(a, np.ndarray):
+            assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+            return a.ctypes.data
+        return a.data_ptr()  # torch tensor
+
+    def upload(self, fine_source, fine_flux, sigT):
+        _check(lib.smk_upload(self._h, self._ptr(fine_source), self._ptr(fine_flux), self._ptr(sigT)))
+
+    def fill_device(self, sigt_floor: float = 0.0):
+        _check(lib.smk_fill_device(self._h, sigt_floor))
+
+    def reset_tallies(self):
+        _check(lib.smk_reset_tallies(self._h))
+
+    def set_stream(self, cuda_stream: int):
+        _check(lib.smk_set_stream(self._h, cuda_stream))
+
+    def run(self, track_begin: int = 0, track_end: int | None = None) -> float:
+        """Synchronous; returns the CUDA-event time of the kernel in seconds."""
+        t = C.c_double(0.0)
+        te = self.n_tracks if track_end is None else track_end
+        _check(lib.smk_run(self._h, track_begin, te, C.byref(t)))
+        return t.value
+
+    def run_async(self, track_begin: int = 0, track_end: int | None = None):
+        te = self.n_tracks if track_end is None else track_end
+        _check(lib.smk_run_async(self._h, track_begin, te))
+
+    def synchronize(self):
+        _check(lib.smk_synchronize(self._h))
+
+    def download_flux(self, out=None):
+        if out is None:
+            out = np.empty((self.R, self.F, self.G), np.float32)
+        _check(lib.smk_download_flux(self._h, self._ptr(out)))
+        return out
+
+    def download_psi(self, n_tracks: int):
+        out = np.empty((n_tracks, self.G), np.float32)
+        _check(lib.smk_download_psi(self._h, out.ctypes.data))
+        return out
+
+    def checksum(self) -> int:
+        v = C.c_uint64(0)
+        _check(lib.smk_download_checksum(self._h, C.byref(v)))
+        return v.value
+
+    @property
+    def launch_count(self) -> int:
+        return lib.smk_launch_count(self._h)
+
+    # raw device pointers for torch / NCCL plumbing
+    @property
+    def tally_ptr(self) -> int:
+        return lib.smk_device_tally(self._h)
+
+    @property
+    def padded_elems(self) -> int:
+        return lib.smk_padded_elems(self._h)
+
+
+def run_kernel(I: Input, fine_source: np.ndarray, fine_flux: np.ndarray, sigT: np.ndarray):
+    """Drop-in for run_kernel(I, S, table) (kernel.c:3-73) with host slabs: fine_flux is
+    updated in place.  Returns (kernel_seconds, total_seconds)."""
+    p = I.params()
+    ks, ts = C.c_double(0.0), C.c_double(0.0)
+    _check(lib.smk_run_host(C.byref(p), fine_source.ctypes.data, fine_flux.ctypes.data,
+                            sigT.ctypes.data, C.byref(ks), C.byref(ts)))
+    return ks.value, ts.value
+
+
+def debug_exp(exp_mode: str, tau: np.ndarray, device: int = 0) -> np.ndarray:
+    tau = np.ascontiguousarray(tau, np.float32)
+    out = np.empty_like(tau)
+    _check(lib.smk_debug_exp(EXP_MODES[exp_mode], tau, out, tau.size, device))
+    return out
+
+
+def debug_segment_ids(I: Input, seg_begin: int, n: int):
+    p = I.params()
+    q = np.empty(n, np.int32)
+    f = np.empty(n, np.int32)
+    _check(lib.smk_debug_segment_ids(C.byref(p), seg_begin, n, q, f))
+    return q, f
+
+
+def device_count() -> int:
+    return lib.smk_device_count()
+
+
+def alloc_pinned(shape, dtype=np.float32) -> np.ndarray:
+    """numpy view of cudaMallocHost memory (never freed explicitly: lives for the process)."""
+    n = int(np.prod(shape))
+    ptr = lib.smk_alloc_host(n * np.dtype(dtype).itemsize)
+    if not ptr:
+        raise SmkError(lib.smk_last_error().decode())
+    buf = (C.c_byte * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)

@@ -1,0 +1,609 @@
+// smk_api.cu -- implementation of the C ABI declared in include/smk.h.
+//
+// Host side of the path: owns the padded device arrays, the stream and the events,
+// picks the kernel instantiation for (G, math mode, exp mode) and sizes the grid as
+// a multiple of the SM count (persistent CTAs striding over tracks).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/smk.h"
+#include "smk_kernels.cuh"
+
+namespace smk {
+
+// 2^(i/32) as IEEE binary64 bit patterns with i << 47 subtracted (glibc __exp2f_data.tab)
+static const uint64_t h_exp2f_tab[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull,
+};
+
+static thread_local char t_error[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_error, sizeof(t_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define SMK_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(SMK_ECUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,      \
+                        cudaGetErrorString(e_));                                            \
+    } while (0)
+
+// The reference's table (init.c:81-117, called as buildExponentialTable(0.01, 10.0, I),
+// main.c:33): same expressions, same types, evaluated on the host in IEEE arithmetic.
+static void build_exp_table(ExpTable &t)
+{
+    const float precision = 0.01f, maxVal = 10.0f;
+    const int N = (int)(maxVal * std::sqrt(1.0 / (8.0 * precision * 0.01)));   // 353
+    const float dx = maxVal / (float)N;
+    for (int n = 0; n < kTableN; ++n) {
+        const float ex = (float)std::exp((double)(-n * dx));
+        t.pairs[n].x = -ex;
+        t.pairs[n].y = 1 + (n * dx - 1) * ex;
+    }
+    t.dx = dx;
+    t.maxVal = maxVal - dx;
+    (void)N;
+}
+
+struct Shape {
+    int groups_pad;   // floats per padded row
+    int lpt;          // lanes per track
+    int nchunk;       // float4 per lane per row
+};
+
+static bool shape_for(int groups, Shape &s)
+{
+    if (groups < 1) return false;
+    int f4 = (groups + 3) / 4;
+    if (f4 <= 32) {
+        int l = 1;
+        while (l < f4) l <<= 1;
+        s.lpt = l;
+        s.nchunk = 1;
+    } else {
+        int c = (f4 + 31) / 32;
+        int n = 2;
+        while (n < c) n <<= 1;
+        if (n > 8) return false;
+        s.lpt = 32;
+        s.nchunk = n;
+    }
+    s.groups_pad = 4 * s.lpt * s.nchunk;
+    return true;
+}
+
+typedef void (*AttenuateFn)(const KernelArgs);
+
+template <int LPT, int NCHUNK>
+static AttenuateFn pick_modes(int math, int expm)
+{
+#define SMK_PICK(M, E) \
+    if (math == M && expm == E) return attenuate_tracks<LPT, NCHUNK, M, E>;
+    SMK_PICK(kMathFast, kExpPoly)
+    SMK_PICK(kMathFast, kExpMufu)
+    SMK_PICK(kMathFast, kExpGlibc)
+    SMK_PICK(kMathFast, kExpTable)
+    SMK_PICK(kMathStrict, kExpPoly)
+    SMK_PICK(kMathStrict, kExpMufu)
+    SMK_PICK(kMathStrict, kExpGlibc)
+    SMK_PICK(kMathStrict, kExpTable)
+#undef SMK_PICK
+    return nullptr;
+}
+
+static AttenuateFn pick_kernel(const Shape &s, int math, int expm)
+{
+    if (s.nchunk == 1) {
+        switch (s.lpt) {
+            case 1: return pick_modes<1, 1>(math, expm);
+            case 2: return pick_modes<2, 1>(math, expm);
+            case 4: return pick_modes<4, 1>(math, expm);
+            case 8: return pick_modes<8, 1>(math, expm);
+            case 16: return pick_modes<16, 1>(math, expm);
+            case 32: return pick_modes<32, 1>(math, expm);
+        }
+    } else if (s.lpt == 32) {
+        switch (s.nchunk) {
+            case 2: return pick_modes<32, 2>(math, expm);
+            case 4: return pick_modes<32, 4>(math, expm);
+            case 8: return pick_modes<32, 8>(math, expm);
+        }
+    }
+    return nullptr;
+}
+
+}  // namespace smk
+
+using namespace smk;
+
+struct smk_ctx {
+    smk_params p;
+    Shape shape;
+    AttenuateFn kernel;
+    int sm_count;
+    int blocks_per_sm;
+    int64_t rows;            // R * F
+    int64_t n_tracks;
+    float *d_source, *d_sigT, *d_flux0, *d_tally;
+    float *d_stage;          // unpadded staging, R*F*G floats
+    float *d_psi;            // [tracks of last run][G_pad] (SMK_FLAG_KEEP_PSI)
+    int64_t psi_capacity;    // in tracks
+    int64_t last_begin, last_end;
+    unsigned long long *d_checksum;
+    cudaStream_t stream;
+    bool own_stream;
+    cudaEvent_t ev0, ev1;
+    bool have_data;
+    int64_t launches;
+};
+
+static int validate(const smk_params *p, Shape &shape)
+{
+    if (!p) return fail(SMK_EINVAL, "params is NULL");
+    if (p->source_3D_regions < 1) return fail(SMK_EINVAL, "source_3D_regions must be >= 1");
+    if (p->fine_axial_intervals < 2)
+        return fail(SMK_EINVAL, "fine_axial_intervals must be >= 2 (kernel.c:111-137 reads row FAI+1 / FAI-1)");
+    if (p->egroups < 1) return fail(SMK_EINVAL, "egroups must be >= 1");
+    if (p->seg_per_track < 1) return fail(SMK_EINVAL, "seg_per_track must be >= 1");
+    if (p->segments < 0) return fail(SMK_EINVAL, "segments must be >= 0");
+    if (p->exp_mode < SMK_EXP_POLY || p->exp_mode > SMK_EXP_TABLE)
+        return fail(SMK_EINVAL, "unknown exp_mode %d", p->exp_mode);
+    if (p->math_mode != SMK_MATH_FAST && p->math_mode != SMK_MATH_STRICT)
+        return fail(SMK_EINVAL, "unknown math_mode %d", p->math_mode);
+    if (!shape_for(p->egroups, shape))
+        return fail(SMK_EINVAL, "egroups = %d unsupported (max 1024)", p->egroups);
+    if ((int64_t)p->source_3D_regions * p->fine_axial_intervals >= (1ll << 31))
+        return fail(SMK_EINVAL, "regions * intervals must be < 2^31");
+    return SMK_OK;
+}
+
+extern "C" {
+
+int smk_abi_version(void) { return SMK_ABI_VERSION; }
+
+const char *smk_last_error(void) { return t_error; }
+
+int smk_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int smk_device_name(int device, char *buf, size_t buflen)
+{
+    if (!buf || buflen == 0) return fail(SMK_EINVAL, "buf is NULL");
+    cudaDeviceProp prop;
+    SMK_CUDA(cudaGetDeviceProperties(&prop, device));
+    snprintf(buf, buflen, "%s", prop.name);
+    return SMK_OK;
+}
+
+int smk_padded_groups(int egroups)
+{
+    Shape s;
+    return shape_for(egroups, s) ? s.groups_pad : SMK_EINVAL;
+}
+
+int64_t smk_num_tracks(int64_t segments, int seg_per_track)
+{
+    if (segments < 0 || seg_per_track < 1) return SMK_EINVAL;
+    return (segments + seg_per_track - 1) / seg_per_track;
+}
+
+int smk_create(const smk_params *p, smk_ctx **out)
+{
+    if (!out) return fail(SMK_EINVAL, "out is NULL");
+    *out = nullptr;
+    Shape shape;
+    int rc = validate(p, shape);
+    if (rc != SMK_OK) return rc;
+    int ndev = 0;
+    SMK_CUDA(cudaGetDeviceCount(&ndev));
+    if (p->device < 0 || p->device >= ndev)
+        return fail(SMK_EINVAL, "device %d out of range (%d visible)", p->device, ndev);
+    SMK_CUDA(cudaSetDevice(p->device));
+
+    smk_ctx *c = new (std::nothrow) smk_ctx();
+    if (!c) return fail(SMK_ENOMEM, "out of host memory");
+    memset(c, 0, sizeof(*c));
+    c->p = *p;
+    c->shape = shape;
+    c->kernel = pick_kernel(shape, p->math_mode, p->exp_mode);
+    if (!c->kernel) {
+        delete c;
+        return fail(SMK_EINVAL, "no kernel for egroups=%d math=%d exp=%d", p->egroups, p->math_mode,
+                    p->exp_mode);
+    }
+    c->rows = (int64_t)p->source_3D_regions * p->fine_axial_intervals;
+    c->n_tracks = smk_num_tracks(p->segments, p->seg_per_track);
+
+    cudaDeviceProp prop;
+    SMK_CUDA(cudaGetDeviceProperties(&prop, p->device));
+    c->sm_count = prop.multiProcessorCount;
+    SMK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->blocks_per_sm, c->kernel,
+                                                           kThreadsPerBlock, 0));
+    if (c->blocks_per_sm < 1) c->blocks_per_sm = 1;
+
+    ExpTable tab;
+    build_exp_table(tab);
+    SMK_CUDA(cudaMemcpyToSymbol(c_exp_table, &tab, sizeof(tab)));
+    SMK_CUDA(cudaMemcpyToSymbol(c_exp2f_tab, h_exp2f_tab, sizeof(h_exp2f_tab)));
+
+    const size_t slab = (size_t)c->rows * shape.groups_pad * sizeof(float);
+    const size_t sig = (size_t)p->source_3D_regions * shape.groups_pad * sizeof(float);
+    const size_t stage = (size_t)c->rows * p->egroups * sizeof(float);
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_source, slab);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_flux0, slab);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_tally, slab);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_sigT, sig);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_stage, stage);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_checksum, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) { c->own_stream = true; e = cudaEventCreate(&c->ev0); }
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tally, 0, slab, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_flux0, 0, slab, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_checksum, 0, sizeof(unsigned long long), c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        int code = (e == cudaErrorMemoryAllocation) ? SMK_ENOMEM : SMK_ECUDA;
+        fail(code, "smk_create: %s", cudaGetErrorString(e));
+        smk_destroy(c);
+        return code;
+    }
+    *out = c;
+    return SMK_OK;
+}
+
+void smk_destroy(smk_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->p.device);
+    cudaFree(c->d_source);
+    cudaFree(c->d_flux0);
+    cudaFree(c->d_tally);
+    cudaFree(c->d_sigT);
+    cudaFree(c->d_stage);
+    cudaFree(c->d_psi);
+    cudaFree(c->d_checksum);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int smk_set_stream(smk_ctx *c, void *cuda_stream)
+{
+    if (!c) return fail(SMK_EINVAL, "ctx is NULL");
+    SMK_CUDA(cudaSetDevice(c->p.device));
+    SMK_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+    return SMK_OK;
+}
+
+static int layout_grid(int64_t n)
+{
+    int64_t b = (n + 255) / 256;
+    return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
+}
+
+// host unpadded -> device padded, through the unpadded staging buffer when G != G_pad
+static int upload_rows(smk_ctx *c, const float *h, float *d, int64_t rows, float pad)
+{
+    const int G = c->p.egroups, Gp = c->shape.groups_pad;
+    if (G == Gp) {
+        SMK_CUDA(cudaMemcpyAsync(d, h, (size_t)rows * G * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    } else {
+        SMK_CUDA(cudaMemcpyAsync(c->d_stage, h, (size_t)rows * G * sizeof(float), cudaMemcpyHostToDevice,
+                                 c->stream));
+        pad_rows<<<layout_grid(rows * Gp), 256, 0, c->stream>>>(c->d_stage, d, rows, G, Gp, pad);
+        SMK_CUDA(cudaGetLastError());
+    }
+    return SMK_OK;
+}
+
+int smk_reset_tallies(smk_ctx *c)
+{
+    if (!c) return fail(SMK_EINVAL, "ctx is NULL");
+    SMK_CUDA(cudaSetDevice(c->p.device));
+    SMK_CUDA(cudaMemsetAsync(c->d_tally, 0, (size_t)c->rows * c->shape.groups_pad * sizeof(float), c->stream));
+    SMK_CUDA(cudaMemsetAsync(c->d_checksum, 0, sizeof(unsigned long long), c->stream));
+    return SMK_OK;
+}
+
+int smk_upload(smk_ctx *c, const float *fine_source, const float *fine_flux, const float *sigT)
+{
+    if (!c) return fail(SMK_EINVAL, "ctx is NULL");
+    if (!fine_source || !sigT) return fail(SMK_EINVAL, "fine_source and sigT are required");
+    SMK_CUDA(cudaSetDevice(c->p.device));
+    int rc;
+    if ((rc = upload_rows(c, fine_source, c->d_source, c->rows, 0.0f)) != SMK_OK) return rc;
+    if ((rc = upload_rows(c, sigT, c->d_sigT, c->p.source_3D_regions, 1.0f)) != SMK_OK) return rc;
+    if (fine_flux) {
+        if ((rc = upload_rows(c, fine_flux, c->d_flux0, c->rows, 0.0f)) != SMK_OK) return rc;
+    } else {
+        SMK_CUDA(cudaMemsetAsync(c->d_flux0, 0, (size_t)c->rows * c->shape.groups_pad * sizeof(float), c->stream));
+    }
+    if ((rc = smk_reset_tallies(c)) != SMK_OK) return rc;
+    SMK_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_data = true;
+    return SMK_OK;
+}
+
+int smk_fill_device(smk_ctx *c, float sigt_floor)
+{
+    if (!c) return fail(SMK_EINVAL, "ctx is NULL");
+    if (!(sigt_floor >= 0.0f && sigt_floor < 1.0f)) return fail(SMK_EINVAL, "sigt_floor must be in [0, 1)");
+    SMK_CUDA(cudaSetDevice(c->p.device));
+    const int G = c->p.egroups, Gp = c->shape.groups_pad;
+    const int64_t R = c->p.source_3D_regions;
+    fill_rows<<<layout_grid(c->rows * Gp), 256, 0, c->stream>>>(c->d_source, c->rows, G, Gp, 0u, c->p.seed, 0.0f, 0.0f);
+    fill_rows<<<layout_grid(c->rows * Gp), 256, 0, c->stream>>>(c->d_flux0, c->rows, G, Gp, 1u, c->p.seed, 0.0f, 0.0f);
+    fill_rows<<<layout_grid(R * Gp), 256, 0, c->stream>>>(c->d_sigT, R, G, Gp, 2u, c->p.seed, sigt_floor, 1.0f);
+    SMK_CUDA(cudaGetLastError());
+    c->launches += 3;
+    int rc = smk_reset_tallies(c);
+    if (rc != SMK_OK) return rc;
+    SMK_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_data = true;
+    return SMK_OK;
+}
+
+static int launch(smk_ctx *c, int64_t track_begin, int64_t track_end)
+{
+    if (!c) return fail(SMK_EINVAL, "ctx is NULL");
+    if (!c->have_data) return fail(SMK_ESTATE, "no source data: call smk_upload or smk_fill_device first");
+    if (track_begin < 0 || track_end > c->n_tracks || track_begin > track_end)
+        return fail(SMK_EINVAL, "track range [%lld, %lld) outside [0, %lld)", (long long)track_begin,
+                    (long long)track_end, (long long)c->n_tracks);
+    SMK_CUDA(cudaSetDevice(c->p.device));
+    c->last_begin = track_begin;
+    c->last_end = track_end;
+    const int64_t tracks = track_end - track_begin;
+    if (tracks == 0) return SMK_OK;
+
+    if (c->p.flags & SMK_FLAG_KEEP_PSI) {
+        if (tracks > c->psi_capacity) {
+            cudaFree(c->d_psi);
+            c->d_psi = nullptr;
+            c->psi_capacity = 0;
+            cudaError_t e = cudaMalloc(&c->d_psi, (size_t)tracks * c->shape.groups_pad * sizeof(float));
+            if (e != cudaSuccess) return fail(SMK_ENOMEM, "psi buffer: %s", cudaGetErrorString(e));
+            c->psi_capacity = tracks;
+        }
+    }
+
+    KernelArgs a;
+    a.source = reinterpret_cast<const float4 *>(c->d_source);
+    a.sigT = reinterpret_cast<const float4 *>(c->d_sigT);
+    a.tally = c->d_tally;
+    a.psi_out = (c->p.flags & SMK_FLAG_KEEP_PSI) ? c->d_psi : nullptr;
+    a.checksum = c->d_checksum;
+    a.segments = c->p.segments;
+    a.track_begin = track_begin;
+    a.track_end = track_end;
+    a.seed = c->p.seed;
+    a.mod_regions = make_fastmod((uint32_t)c->p.source_3D_regions);
+    a.mod_fai = make_fastmod((uint32_t)c->p.fine_axial_intervals);
+    a.fai_count = c->p.fine_axial_intervals;
+    a.row_f4 = c->shape.groups_pad / 4;
+    a.seg_per_track = c->p.seg_per_track;
+
+    // persistent grid: a whole number of CTAs per SM, each track slot strides over tracks
+    const int slots_per_block = (kThreadsPerBlock / 32) * (32 / c->shape.lpt);
+    int64_t want = (tracks + slots_per_block - 1) / slots_per_block;
+    int64_t full = (int64_t)c->sm_count * c->blocks_per_sm;
+    int grid = (int)(want < full ? want : full);
+    c->kernel<<<grid, kThreadsPerBlock, 0, c->stream>>>(a);
+    SMK_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return SMK_OK;
+}
+
+int smk_run_async(smk_ctx *c, int64_t track_begin, int64_t track_end)
+{
+    return launch(c, track_begin, track_end);
+}
+
+int smk_synchronize(smk_ctx *c)
+{
+    if (!c) return fail(SMK_EINVAL, "ctx is NULL");
+    SMK_CUDA(cudaSetDevice(c->p.device));
+    SMK_CUDA(cudaStreamSynchronize(c->stream));
+    return SMK_OK;
+}
+
+int smk_run(smk_ctx *c, int64_t track_begin, int64_t track_end, double *kernel_seconds)
+{
+    if (!c) return fail(SMK_EINVAL, "ctx is NULL");
+    SMK_CUDA(cudaSetDevice(c->p.device));
+    SMK_CUDA(cudaEventRecord(c->ev0, c->stream));
+    int rc = launch(c, track_begin, track_end);
+    if (rc != SMK_OK) return rc;
+    SMK_CUDA(cudaEventRecord(c->ev1, c->stream));
+    SMK_CUDA(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    SMK_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (kernel_seconds) *kernel_seconds = (double)ms * 1e-3;
+    return SMK_OK;
+}
+
+int64_t smk_launch_count(const smk_ctx *c) { return c ? c->launches : 0; }
+
+int smk_download_flux(smk_ctx *c, float *out)
+{
+    if (!c || !out) return fail(SMK_EINVAL, "NULL argument");
+    SMK_CUDA(cudaSetDevice(c->p.device));
+    const int G = c->p.egroups, Gp = c->shape.groups_pad;
+    finalize_flux<<<layout_grid(c->rows * G), 256, 0, c->stream>>>(c->d_flux0, c->d_tally, c->d_stage, c->rows, G, Gp);
+    SMK_CUDA(cudaGetLastError());
+    c->launches += 1;
+    SMK_CUDA(cudaMemcpyAsync(out, c->d_stage, (size_t)c->rows * G * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    SMK_CUDA(cudaStreamSynchronize(c->stream));
+    return SMK_OK;
+}
+
+int smk_download_psi(smk_ctx *c, float *psi_out)
+{
+    if (!c || !psi_out) return fail(SMK_EINVAL, "NULL argument");
+    if (!(c->p.flags & SMK_FLAG_KEEP_PSI)) return fail(SMK_ESTATE, "context created without SMK_FLAG_KEEP_PSI");
+    const int64_t tracks = c->last_end - c->last_begin;
+    if (tracks <= 0) return SMK_OK;
+    SMK_CUDA(cudaSetDevice(c->p.device));
+    SMK_CUDA(cudaMemcpy2DAsync(psi_out, (size_t)c->p.egroups * sizeof(float), c->d_psi,
+                               (size_t)c->shape.groups_pad * sizeof(float),
+                               (size_t)c->p.egroups * sizeof(float), (size_t)tracks,
+                               cudaMemcpyDeviceToHost, c->stream));
+    SMK_CUDA(cudaStreamSynchronize(c->stream));
+    return SMK_OK;
+}
+
+int smk_download_checksum(smk_ctx *c, uint64_t *checksum)
+{
+    if (!c || !checksum) return fail(SMK_EINVAL, "NULL argument");
+    SMK_CUDA(cudaSetDevice(c->p.device));
+    unsigned long long v = 0;
+    SMK_CUDA(cudaMemcpyAsync(&v, c->d_checksum, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    SMK_CUDA(cudaStreamSynchronize(c->stream));
+    *checksum = (uint64_t)v;
+    return SMK_OK;
+}
+
+int smk_run_host(const smk_params *p, const float *fine_source, float *fine_flux, const float *sigT,
+                 double *kernel_seconds, double *total_seconds)
+{
+    if (!fine_flux) return fail(SMK_EINVAL, "fine_flux is required (updated in place)");
+    smk_ctx *c = nullptr;
+    int rc = smk_create(p, &c);
+    if (rc != SMK_OK) return rc;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    cudaEventRecord(t0, c->stream);
+    rc = smk_upload(c, fine_source, fine_flux, sigT);
+    if (rc == SMK_OK) rc = smk_run(c, 0, c->n_tracks, kernel_seconds);
+    if (rc == SMK_OK) rc = smk_download_flux(c, fine_flux);
+    if (rc == SMK_OK) {
+        cudaEventRecord(t1, c->stream);
+        cudaEventSynchronize(t1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t0, t1);
+        if (total_seconds) *total_seconds = (double)ms * 1e-3;
+    }
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    smk_destroy(c);
+    return rc;
+}
+
+void *smk_device_tally(smk_ctx *c) { return c ? c->d_tally : nullptr; }
+void *smk_device_flux0(smk_ctx *c) { return c ? c->d_flux0 : nullptr; }
+void *smk_device_source(smk_ctx *c) { return c ? c->d_source : nullptr; }
+void *smk_device_sigT(smk_ctx *c) { return c ? c->d_sigT : nullptr; }
+int64_t smk_padded_elems(const smk_ctx *c) { return c ? c->rows * c->shape.groups_pad : 0; }
+
+void *smk_alloc_host(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        fail(SMK_ENOMEM, "cudaMallocHost(%zu) failed", bytes);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void smk_free_host(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int smk_debug_exp(int exp_mode, const float *tau, float *out, int64_t n, int device)
+{
+    if (!tau || !out || n < 0) return fail(SMK_EINVAL, "bad argument");
+    if (n == 0) return SMK_OK;
+    SMK_CUDA(cudaSetDevice(device));
+    ExpTable tab;
+    build_exp_table(tab);
+    SMK_CUDA(cudaMemcpyToSymbol(c_exp_table, &tab, sizeof(tab)));
+    SMK_CUDA(cudaMemcpyToSymbol(c_exp2f_tab, h_exp2f_tab, sizeof(h_exp2f_tab)));
+    float *d_in = nullptr, *d_out = nullptr;
+    SMK_CUDA(cudaMalloc(&d_in, (size_t)n * sizeof(float)));
+    cudaError_t e = cudaMalloc(&d_out, (size_t)n * sizeof(float));
+    if (e != cudaSuccess) {
+        cudaFree(d_in);
+        return fail(SMK_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    cudaMemcpy(d_in, tau, (size_t)n * sizeof(float), cudaMemcpyHostToDevice);
+    const int grid = layout_grid(n);
+    switch (exp_mode) {
+        case SMK_EXP_POLY: debug_exp_kernel<kExpPoly><<<grid, 256>>>(d_in, d_out, n); break;
+        case SMK_EXP_MUFU: debug_exp_kernel<kExpMufu><<<grid, 256>>>(d_in, d_out, n); break;
+        case SMK_EXP_GLIBC: debug_exp_kernel<kExpGlibc><<<grid, 256>>>(d_in, d_out, n); break;
+        case SMK_EXP_TABLE: debug_exp_kernel<kExpTable><<<grid, 256>>>(d_in, d_out, n); break;
+        default:
+            cudaFree(d_in);
+            cudaFree(d_out);
+            return fail(SMK_EINVAL, "unknown exp_mode %d", exp_mode);
+    }
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(SMK_ECUDA, "debug_exp: %s", cudaGetErrorString(e));
+    return SMK_OK;
+}
+
+int smk_debug_segment_ids(const smk_params *p, int64_t seg_begin, int64_t n, int32_t *qsr_out, int32_t *fai_out)
+{
+    Shape shape;
+    int rc = validate(p, shape);
+    if (rc != SMK_OK) return rc;
+    if (!qsr_out || !fai_out || n < 0 || seg_begin < 0) return fail(SMK_EINVAL, "bad argument");
+    if (n == 0) return SMK_OK;
+    SMK_CUDA(cudaSetDevice(p->device));
+    int32_t *d_q = nullptr, *d_f = nullptr;
+    SMK_CUDA(cudaMalloc(&d_q, (size_t)n * sizeof(int32_t)));
+    cudaError_t e = cudaMalloc(&d_f, (size_t)n * sizeof(int32_t));
+    if (e != cudaSuccess) {
+        cudaFree(d_q);
+        return fail(SMK_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    debug_ids_kernel<<<layout_grid(n), 256>>>(p->seed, seg_begin, n, make_fastmod((uint32_t)p->source_3D_regions),
+                                             make_fastmod((uint32_t)p->fine_axial_intervals), d_q, d_f);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(qsr_out, d_q, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(fai_out, d_f, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d_q);
+    cudaFree(d_f);
+    if (e != cudaSuccess) return fail(SMK_ECUDA, "debug_segment_ids: %s", cudaGetErrorString(e));
+    return SMK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,266 @@
+// smk_math.cuh -- per-intersection arithmetic of attenuate_segment
+// (/root/reference/src/cpu/kernel.c:75-333) for one (segment, energy group).
+//
+// Two arithmetic modes (include/smk.h):
+//   STRICT  every operation of the reference, in its order, with IEEE round-to-nearest
+//           intrinsics (never contracted): bit-identical per intersection to a
+//           -O2 -ffp-contract=off build of kernel.c.  Verification mode.
+//   FAST    the same formulae with the constants folded into the quadratic-fit
+//           coefficients, FMA contraction and one MUFU.RCP replacing the five divides
+//           (kernel.c:236,249,251,291,301).  Throughput mode; checked against the
+//           oracle by the L2-relative gate of DESIGN.md section 6.
+//
+// Four evaluations of e = exp(-tau) (kernel.c:221), see exp_neg<>.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace smk {
+
+// placeholder geometry of the mini-app, kernel.c:99-104
+struct Geometry {
+    static constexpr float dz = 0.1f;
+    static constexpr float zin = 0.3f;
+    static constexpr float weight = 0.5f;
+    static constexpr float mu = 0.9f;
+    static constexpr float mu2 = 0.3f;
+    static constexpr float ds = 0.7f;
+};
+
+enum : int { kExpPoly = 0, kExpMufu = 1, kExpGlibc = 2, kExpTable = 3 };
+enum : int { kMathFast = 0, kMathStrict = 1 };
+
+// --------------------------------------------------------------------------
+// Exponential table of the reference (init.c:81-117): 353 {slope, intercept}
+// pairs, dx = 10/353, maxVal = 10 - dx.  tau = 0.7*sigT < 0.7 only ever reaches
+// the first 25 intervals; the kernel keeps kTableReach pairs in shared memory.
+// --------------------------------------------------------------------------
+constexpr int kTableN = 353;
+constexpr int kTableReach = 32;
+struct ExpTable {
+    float2 pairs[kTableN];   // .x = slope, .y = intercept
+    float dx;
+    float maxVal;
+};
+// (defined here: this header is included by exactly one translation unit, smk_api.cu)
+__constant__ ExpTable c_exp_table;
+
+// 2^(i/32) bit patterns minus (i << 47): the 32-entry table of glibc's expf
+// (sysdeps/ieee754/flt-32/math_config.h, __exp2f_data.tab; glibc 2.39).
+__constant__ uint64_t c_exp2f_tab[32];
+
+// e = exp(-tau) the way glibc 2.39's x86-64 FMA variant of expf computes it
+// (sysdeps/ieee754/flt-32/e_expf.c built with -mfma -mavx2; verified against the
+// disassembly of __expf_fma in this image's libm): double arithmetic, N = 32,
+// degree-3 polynomial, fused multiply-adds where gcc contracted them.
+__device__ __forceinline__ float expf_glibc(float x)
+{
+    const double InvLn2N = 0x1.71547652b82fep+5;   // 32 / ln 2
+    const double Shift = 0x1.8p+52;
+    const double C0 = 0x1.c6af84b912394p-20;       // 0x1.c6af84b912394p-5 / 32^3
+    const double C1 = 0x1.ebfce50fac4f3p-13;       // 0x1.ebfce50fac4f3p-3 / 32^2
+    const double C2 = 0x1.62e42ff0c52d6p-6;        // 0x1.62e42ff0c52d6p-1 / 32
+    const double xd = (double)x;
+    double kd = __fma_rn(InvLn2N, xd, Shift);
+    const uint64_t ki = (uint64_t)__double_as_longlong(kd);
+    kd = __dsub_rn(kd, Shift);
+    const double r = __fma_rn(InvLn2N, xd, -kd);
+    uint64_t t = c_exp2f_tab[ki & 31u];
+    t += ki << 47;
+    const double s = __longlong_as_double((long long)t);
+    const double z = __fma_rn(C0, r, C1);
+    const double r2 = __dmul_rn(r, r);
+    double y = __fma_rn(C2, r, 1.0);
+    y = __fma_rn(z, r2, y);
+    y = __dmul_rn(y, s);
+    return __double2float_rn(y);
+}
+
+// e = RN(1 + x + x^2 P(x)), x = -tau in [-0.7, 0], with the rounding error of 1 + x
+// carried into the last addition (Fast2Sum), so that e equals the correctly rounded
+// exp(x) wherever 1 - e is ill-conditioned (|x| small): exhaustive sweep against
+// glibc expf over all 1.06e9 binary32 tau in (0, 0.7]: 0 mismatches for tau < 2^-14,
+// <= 1 ulp everywhere (tests/test_expf.py, profiles/expf_sweep_r01.md).
+__device__ __forceinline__ float exp_poly(float x)
+{
+    float p = 0x1.415ffep-13f;
+    p = __fmaf_rn(p, x, 0x1.6336e4p-10f);
+    p = __fmaf_rn(p, x, 0x1.10ac84p-7f);
+    p = __fmaf_rn(p, x, 0x1.555146p-5f);
+    p = __fmaf_rn(p, x, 0x1.555546p-3f);
+    p = __fmaf_rn(p, x, 0.5f);
+    const float x2 = __fmul_rn(x, x);
+    const float s = __fadd_rn(1.0f, x);
+    const float lost = __fsub_rn(x, __fsub_rn(s, 1.0f));   // exact: (1 + x) - s
+    return __fadd_rn(s, __fmaf_rn(x2, p, lost));
+}
+
+__device__ __forceinline__ float exp_mufu(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+}
+
+__device__ __forceinline__ float rcp_mufu(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// interpolateTable, kernel.c:337-361, against pairs staged in shared memory
+__device__ __forceinline__ float table_lookup(const float2 *__restrict__ s_pairs, float dx,
+                                              float maxVal, float x)
+{
+    if (x > maxVal) return 1.0f;
+    int interval = (int)__fadd_rn(__fdiv_rn(x, dx), __fmul_rn(0.5f, dx));
+    const float2 si = (interval < kTableReach) ? s_pairs[interval] : c_exp_table.pairs[interval];
+    return __fadd_rn(__fmul_rn(si.x, x), si.y);
+}
+
+// expVal = 1 - exp(-tau) (kernel.c:221) or its table replacement (kernel.c:219).
+// *e_out receives exp(-tau) itself where it is available (FAST reuses it for t4).
+template <int EXPM>
+__device__ __forceinline__ float exp_val(float tau, const float2 *s_pairs, float &e_out)
+{
+    if constexpr (EXPM == kExpTable) {
+        const float ev = table_lookup(s_pairs, c_exp_table.dx, c_exp_table.maxVal, tau);
+        e_out = __fsub_rn(1.0f, ev);
+        return ev;
+    } else {
+        float e;
+        if constexpr (EXPM == kExpPoly) e = exp_poly(-tau);
+        else if constexpr (EXPM == kExpMufu) e = exp_mufu(-tau);
+        else e = expf_glibc(-tau);
+        e_out = e;
+        return __fsub_rn(1.0f, e);
+    }
+}
+
+// --------------------------------------------------------------------------
+// Quadratic / linear axial source fit (kernel.c:111-191) as coefficients of
+// (y1, y2, y3) = fine_source[QSR][FAI-1 .. FAI+1][g], constants folded:
+//   interior : q0 = 6 y1 - 8 y2 + 3 y3, q1 = 35 y1 - 60 y2 + 25 y3, q2 = 50 (y1 - 2 y2 + y3)
+//   FAI == 0 : q0 = -2 y2 + 3 y3,       q1 = 10 (y3 - y2),          q2 = 0
+//   FAI == F-1: q0 = -3 y1 + 4 y2,      q1 = 10 (y2 - y1),          q2 = 0
+// (dz = 0.1, zin = 0.3).  q1 and q2 are returned pre-multiplied by mu and mu2.
+// --------------------------------------------------------------------------
+struct FitCoeffs {
+    float a0, b0, c0;   // q0
+    float a1, b1, c1;   // mu  * q1
+    float a2, b2, c2;   // mu2 * q2
+};
+
+__device__ __forceinline__ FitCoeffs fit_coeffs(bool first, bool last)
+{
+    constexpr float dz = Geometry::dz, zin = Geometry::zin;
+    constexpr float mu = Geometry::mu, mu2 = Geometry::mu2;
+    // interior: c1 = (y1 - y3) / (2 dz), c2 = (y1 - 2 y2 + y3) / (2 dz^2)
+    constexpr float k1 = 1.0f / (2.0f * dz), k2 = 1.0f / (2.0f * dz * dz);
+    constexpr float ia0 = k1 * zin + k2 * zin * zin, ib0 = 1.0f - 2.0f * k2 * zin * zin,
+                    ic0 = -k1 * zin + k2 * zin * zin;
+    constexpr float ia1 = mu * (k1 + 2.0f * k2 * zin), ib1 = mu * (-4.0f * k2 * zin),
+                    ic1 = mu * (-k1 + 2.0f * k2 * zin);
+    constexpr float ia2 = mu2 * k2, ib2 = mu2 * -2.0f * k2, ic2 = mu2 * k2;
+    // edges: c1 = (y3 - y2) / dz resp. (y2 - y1) / dz
+    constexpr float e = 1.0f / dz;
+    FitCoeffs f;
+    f.a0 = first ? 0.0f : (last ? -e * zin : ia0);
+    f.b0 = first ? 1.0f - e * zin : (last ? 1.0f + e * zin : ib0);
+    f.c0 = first ? e * zin : (last ? 0.0f : ic0);
+    f.a1 = first ? 0.0f : (last ? -mu * e : ia1);
+    f.b1 = first ? -mu * e : (last ? mu * e : ib1);
+    f.c1 = first ? mu * e : (last ? 0.0f : ic1);
+    const bool edge = first || last;
+    f.a2 = edge ? 0.0f : ia2;
+    f.b2 = edge ? 0.0f : ib2;
+    f.c2 = edge ? 0.0f : ic2;
+    return f;
+}
+
+// FAST: one intersection.  y1 / y3 must be finite (0) when the row is not loaded.
+template <int EXPM>
+__device__ __forceinline__ void attenuate_fast(const FitCoeffs &f, float y1, float y2, float y3,
+                                               float sigT, const float2 *s_pairs, float &psi,
+                                               float &tally)
+{
+    const float q0 = fmaf(f.c0, y3, fmaf(f.b0, y2, f.a0 * y1));
+    const float Q1 = fmaf(f.c1, y3, fmaf(f.b1, y2, f.a1 * y1));   // mu  * q1
+    const float Q2 = fmaf(f.c2, y3, fmaf(f.b2, y2, f.a2 * y1));   // mu2 * q2
+
+    const float tau = sigT * Geometry::ds;
+    float e;
+    const float ev = exp_val<EXPM>(tau, s_pairs, e);
+
+    const float rs = rcp_mufu(sigT);
+    const float rs2 = rs * rs;
+    // reuse = tau (tau - 2) + 2 expVal / sigT^3           (kernel.c:235-236)
+    const float reuse = fmaf(2.0f, ev * (rs2 * rs), tau * (tau - 2.0f));
+    // (q0 tau + (sigT psi - q0) expVal) / sigT^2          (kernel.c:248-249)
+    const float n1 = fmaf(fmaf(sigT, psi, -q0), ev, q0 * tau);
+    // tau (tau (tau - 3) + 6) - 6 expVal                  (kernel.c:250)
+    const float p3 = fmaf(tau, fmaf(tau, tau - 3.0f, 6.0f), -6.0f * ev);
+    const float w3 = (Q2 * (1.0f / 3.0f)) * (p3 * (rs2 * rs2));   // kernel.c:250-251
+    const float flux_integral = fmaf(n1, rs2, fmaf(Q1, reuse, w3));
+    tally = Geometry::weight * flux_integral;                      // kernel.c:262
+
+    // psi_out = t1 + t2 + t3 + t4                         (kernel.c:291-331)
+    float acc = (q0 * ev) * rs;
+    acc = fmaf(Q1 * (tau - ev), rs2, acc);
+    acc = fmaf(Q2, reuse, acc);
+    psi = fmaf(psi, e, acc);
+}
+
+// STRICT: one intersection in the reference's own operation order.
+template <int EXPM>
+__device__ __forceinline__ void attenuate_strict(bool first, bool last, float y1, float y2,
+                                                 float y3, float sigT, const float2 *s_pairs,
+                                                 float &psi, float &tally)
+{
+    const float dz = Geometry::dz, zin = Geometry::zin, mu = Geometry::mu, mu2 = Geometry::mu2;
+    float q0, q1, q2;
+    if (first) {                                                    // kernel.c:111-135
+        const float c1 = __fdiv_rn(__fsub_rn(y3, y2), dz);
+        q0 = __fadd_rn(y2, __fmul_rn(c1, zin));
+        q1 = c1;
+        q2 = 0.0f;
+    } else if (last) {                                              // kernel.c:137-161
+        const float c1 = __fdiv_rn(__fsub_rn(y2, y1), dz);
+        q0 = __fadd_rn(y2, __fmul_rn(c1, zin));
+        q1 = c1;
+        q2 = 0.0f;
+    } else {                                                        // kernel.c:163-191
+        const float two_dz = __fmul_rn(2.0f, dz);
+        const float two_dz2 = __fmul_rn(two_dz, dz);
+        const float c1 = __fdiv_rn(__fsub_rn(y1, y3), two_dz);
+        const float c2 = __fdiv_rn(__fadd_rn(__fsub_rn(y1, __fmul_rn(2.0f, y2)), y3), two_dz2);
+        q0 = __fadd_rn(__fadd_rn(y2, __fmul_rn(c1, zin)), __fmul_rn(__fmul_rn(c2, zin), zin));
+        q1 = __fadd_rn(c1, __fmul_rn(__fmul_rn(2.0f, c2), zin));
+        q2 = c2;
+    }
+    const float tau = __fmul_rn(sigT, Geometry::ds);                // kernel.c:206
+    const float sigT2 = __fmul_rn(sigT, sigT);                      // kernel.c:207
+    float e;
+    const float ev = exp_val<EXPM>(tau, s_pairs, e);                // kernel.c:219/221
+
+    const float reuse = __fadd_rn(__fmul_rn(tau, __fsub_rn(tau, 2.0f)),
+                                  __fdiv_rn(__fmul_rn(2.0f, ev), __fmul_rn(sigT, sigT2)));
+    const float term1 = __fdiv_rn(
+        __fadd_rn(__fmul_rn(q0, tau), __fmul_rn(__fsub_rn(__fmul_rn(sigT, psi), q0), ev)), sigT2);
+    const float term2 = __fmul_rn(__fmul_rn(q1, mu), reuse);
+    const float cubic = __fsub_rn(
+        __fmul_rn(tau, __fadd_rn(__fmul_rn(tau, __fsub_rn(tau, 3.0f)), 6.0f)), __fmul_rn(6.0f, ev));
+    const float term3 = __fdiv_rn(__fmul_rn(__fmul_rn(q2, mu2), cubic),
+                                  __fmul_rn(__fmul_rn(3.0f, sigT2), sigT2));
+    const float flux_integral = __fadd_rn(__fadd_rn(term1, term2), term3);  // kernel.c:248-251
+    tally = __fmul_rn(Geometry::weight, flux_integral);                     // kernel.c:262
+
+    const float t1 = __fdiv_rn(__fmul_rn(q0, ev), sigT);                               // :291
+    const float t2 = __fdiv_rn(__fmul_rn(__fmul_rn(q1, mu), __fsub_rn(tau, ev)), sigT2);  // :301
+    const float t3 = __fmul_rn(__fmul_rn(q2, mu2), reuse);                             // :311
+    const float t4 = __fmul_rn(psi, __fsub_rn(1.0f, ev));                              // :321
+    psi = __fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), t4);                             // :331
+}
+
+}  // namespace smk

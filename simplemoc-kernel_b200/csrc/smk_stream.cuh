@@ -1,0 +1,120 @@
+// smk_stream.cuh -- the deterministic counter-based stream.
+//
+// Replaces the reference's time-seeded draws: rand_r() for (QSR_id, FAI_id) and the
+// initial state_flux (/root/reference/src/cpu/kernel.c:15,29-30,47,50; the CUDA
+// reference's per-block XORWOW states, /root/reference/src/cuda/kernel.cu:22,52-60)
+// and rand() for the source slabs (/root/reference/src/cpu/init.c:64-75).
+// Pure 32-bit integer arithmetic, identical on host and device; the CPU oracle
+// restates it independently (oracle/smk_oracle.c) and both are pinned to the
+// Random123 Philox4x32-10 known-answer vectors.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SMK_HD __host__ __device__ __forceinline__
+#else
+#define SMK_HD inline
+#endif
+
+namespace smk {
+
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u;
+constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
+constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
+
+constexpr uint32_t kDomainSegment = 0x5345474Du;  // 'SEGM'
+constexpr uint32_t kDomainPsi     = 0x50534930u;  // 'PSI0'
+constexpr uint32_t kDomainFill    = 0x46494C4Cu;  // 'FILL'
+
+struct u32x4 { uint32_t x, y, z, w; };
+
+SMK_HD void mulhilo(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo)
+{
+#if defined(__CUDA_ARCH__)
+    lo = a * b;
+    hi = __umulhi(a, b);
+#else
+    uint64_t p = (uint64_t)a * b;
+    lo = (uint32_t)p;
+    hi = (uint32_t)(p >> 32);
+#endif
+}
+
+// Philox4x32-10.  The key schedule only depends on the seed, so the compiler
+// hoists the ten bumped keys out of loops.
+SMK_HD u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                           uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo(kPhiloxM0, c0, hi0, lo0);
+        mulhilo(kPhiloxM1, c2, hi1, lo1);
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += kPhiloxW0;
+        k1 += kPhiloxW1;
+    }
+    return u32x4{c0, c1, c2, c3};
+}
+
+SMK_HD u32x4 stream_words(uint64_t seed, uint64_t index, uint32_t sub, uint32_t domain)
+{
+    return philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), sub, domain,
+                         (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// (float) rand() / RAND_MAX of the reference == (float)r * 2^-31, r a 31-bit draw.
+SMK_HD float u01(uint32_t w)
+{
+    return (float)(int32_t)(w >> 1) * 4.656612873077392578125e-10f;  // 2^-31
+}
+
+// n % d for 31-bit n by multiply-high: q = floor(n * M / 2^(31+s)), exact for all
+// n < 2^31 with s = ceil(log2 d), M = floor(2^(31+s) / d) + 1 < 2^32 (Granlund &
+// Montgomery).  `%` itself mirrors kernel.c:47,50.
+struct FastMod {
+    uint32_t d, M, s;
+};
+
+inline FastMod make_fastmod(uint32_t d)
+{
+    FastMod f;
+    f.d = d;
+    uint32_t s = 0;
+    while ((1ull << s) < d) ++s;
+    f.s = s;
+    f.M = (d == 1) ? 0u : (uint32_t)(((1ull << (31 + s)) / d) + 1ull);
+    return f;
+}
+
+SMK_HD uint32_t fastmod(uint32_t n, const FastMod &f)  // n < 2^31
+{
+    if (f.d == 1) return 0u;
+#if defined(__CUDA_ARCH__)
+    uint32_t q = __umulhi(n, f.M) >> (f.s - 1);
+#else
+    uint32_t q = (uint32_t)(((uint64_t)n * f.M) >> 32) >> (f.s - 1);
+#endif
+    return n - q * f.d;
+}
+
+struct SegmentIds { uint32_t qsr, fai; };
+
+SMK_HD SegmentIds segment_ids(uint64_t seed, uint64_t seg, const FastMod &mod_regions,
+                              const FastMod &mod_fai)
+{
+    u32x4 w = stream_words(seed, seg, 0u, kDomainSegment);
+    // words z, w are reserved for per-segment geometry (kernel.c:95-104)
+    return SegmentIds{fastmod(w.x >> 1, mod_regions), fastmod(w.y >> 1, mod_fai)};
+}
+
+// weight of segment s in the indexing fingerprint (include/smk.h: smk_download_checksum)
+SMK_HD uint64_t checksum_term(uint32_t qsr, uint32_t fai, uint32_t fai_count, uint64_t seg)
+{
+    return ((uint64_t)qsr * fai_count + fai + 1u) * ((seg & 0xFFFFu) + 1u);
+}
+
+}  // namespace smk
