@@ -64,6 +64,8 @@ class Oracle:
         L.smk_oracle_table_lookup.restype = C.c_float
         L.smk_oracle_expf.argtypes = [C.c_float]
         L.smk_oracle_expf.restype = C.c_float
+        L.smk_oracle_expf_neg_array.argtypes = [_f32p, _f32p, C.c_int64]
+        L.smk_oracle_expf_neg_array.restype = None
         L.smk_oracle_attenuate_segment.argtypes = [C.c_int, C.c_int, C.c_int, _f32p, _f32p,
                                                    _f32p, _f32p, C.c_int]
         L.smk_oracle_attenuate_segment.restype = None
@@ -110,6 +112,13 @@ class Oracle:
 
     def expf(self, x):
         return self.lib.smk_oracle_expf(x)
+
+    def expf_neg(self, tau):
+        """libm expf(-tau), elementwise."""
+        tau = np.ascontiguousarray(tau, np.float32)
+        out = np.empty_like(tau)
+        self.lib.smk_oracle_expf_neg_array(tau, out, tau.size)
+        return out
 
     # -- math ---------------------------------------------------------------
     def attenuate_segment(self, fai_id, src_region, sigt_region, psi, use_table=False):

@@ -187,6 +187,14 @@ float smk_oracle_table_lookup(const float *values, float dx, float maxVal, float
 /* libm's expf, exposed so tests can compare the GPU's glibc-faithful expf. */
 float smk_oracle_expf(float x) { return expf(x); }
 
+/* out[i] = expf(-tau[i]) with libm, for exhaustive sweeps */
+void smk_oracle_expf_neg_array(const float *tau, float *out, int64_t n)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++)
+        out[i] = expf(-tau[i]);
+}
+
 /* ------------------------------------------------------------------------- */
 /* attenuate_segment, kernel.c:75-333, one group at a time.                    */
 /* The reference stages each sub-expression through a scratch vector and runs  */
