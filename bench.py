@@ -167,19 +167,13 @@ def main_reference(a):
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
-class _DevPtr:
-    """Expose a raw device pointer to torch (NCCL operand) via __cuda_array_interface__."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
-
-
 def main_ours(a):
     import numpy as np
     import torch
     import torch.distributed as dist
 
     import smk_b200 as smk
+    multi = smk.multi
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -197,21 +191,21 @@ def main_ours(a):
                   device=local_rank).finalize()
     R, F = I.source_3D_regions, I.fine_axial_intervals
     nt = I.n_tracks
-    tb, te = rank * nt // world, (rank + 1) * nt // world
-    my_segments = min(te * a.seg_per_track, I.segments) - tb * a.seg_per_track
+    tb, te = multi.shard_tracks(nt, rank, world)
+    my_segments = multi.shard_segments(nt, a.seg_per_track, I.segments, rank, world)
 
     ctx = smk.Context(I)
     stream = torch.cuda.current_stream(dev)
     ctx.set_stream(stream.cuda_stream)
     ctx.fill_device(0.0)
-    tally = torch.as_tensor(_DevPtr(ctx.tally_ptr, ctx.padded_elems), device=dev) if world > 1 else None
+    tally = torch.as_tensor(multi.DevicePointer(ctx.tally_ptr, ctx.padded_elems), device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
     def step():
         ctx.reset_tallies()
         ctx.run_async(tb, te)
         if world > 1:
-            dist.all_reduce(tally)          # tally deltas, once per sweep, over NVLink
+            multi.all_reduce_tallies(tally)  # tally deltas, once per sweep, over NVLink
 
     def barrier():
         if world > 1:
@@ -236,7 +230,7 @@ def main_ours(a):
         ctx.run_async(tb, te)
         kev[k][1].record(stream)
         if world > 1:
-            dist.all_reduce(tally)
+            multi.all_reduce_tallies(tally)
         ev[k][1].record(stream)
     barrier()
     clocks = sampler.stop()
@@ -271,13 +265,12 @@ def main_ours(a):
     src[...] = rng.random(src.shape, dtype=np.float32)
     flux0[...] = rng.random(flux0.shape, dtype=np.float32)
     sig[...] = rng.random(sig.shape, dtype=np.float32)
-    host_out = torch.empty(ctx.padded_elems, dtype=torch.float32).pin_memory() if world > 1 else None
 
     def e2e_step():
         ctx.upload(src, flux0, sig)          # H2D (also zeroes the tally deltas)
         ctx.run_async(tb, te)
         if world > 1:
-            dist.all_reduce(tally)
+            multi.all_reduce_tallies(tally)
         ctx.download_flux(out)               # D2H of flux0 + tallies (synchronises)
 
     e2e_step()
@@ -294,7 +287,6 @@ def main_ours(a):
     e2e_value = float(I.segments) * G * e2e_steps / t.item()
     h2d = src.nbytes + flux0.nbytes + sig.nbytes
     d2h = out.nbytes
-    del host_out
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

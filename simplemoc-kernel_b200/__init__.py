@@ -22,6 +22,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
+from . import multi  # noqa: F401  (sharding + all-reduce plumbing)
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libsmk.so")
 

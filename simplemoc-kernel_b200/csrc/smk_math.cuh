@@ -79,8 +79,8 @@ __device__ __forceinline__ float expf_glibc(float x)
 // e = RN(1 + x + x^2 P(x)), x = -tau in [-0.7, 0], with the rounding error of 1 + x
 // carried into the last addition (Fast2Sum), so that e equals the correctly rounded
 // exp(x) wherever 1 - e is ill-conditioned (|x| small): exhaustive sweep against
-// glibc expf over all 1.06e9 binary32 tau in (0, 0.7]: 0 mismatches for tau < 2^-14,
-// <= 1 ulp everywhere (tests/test_expf.py, profiles/expf_sweep_r01.md).
+// glibc expf over all 2.7e8 binary32 tau in [2^-33, 0.7]: 0 mismatches for tau < 2^-14,
+// <= 1 ulp everywhere (tools/expf_sweep.py, profiles/expf_sweep_r01.md).
 __device__ __forceinline__ float exp_poly(float x)
 {
     float p = 0x1.415ffep-13f;
@@ -200,7 +200,13 @@ __device__ __forceinline__ void attenuate_fast(const FitCoeffs &f, float y1, flo
     // (q0 tau + (sigT psi - q0) expVal) / sigT^2          (kernel.c:248-249)
     const float n1 = fmaf(fmaf(sigT, psi, -q0), ev, q0 * tau);
     // tau (tau (tau - 3) + 6) - 6 expVal                  (kernel.c:250)
-    const float p3 = fmaf(tau, fmaf(tau, tau - 3.0f, 6.0f), -6.0f * ev);
+    // NOT contracted: the true value is ~tau^4/4 while the terms are ~6 tau, so for small
+    // sigT the result is pure rounding noise (cancellation factor 24/tau^3) that is then
+    // divided by 3 sigT^4 and reaches 1e-4 of the dominant term.  Parity with the reference
+    // needs the reference's own roundings here; measured (gpurun r01a, reproduced by CPU
+    // emulation): contracted 1.2e-4 L2-relative, reference order 3.6e-8.
+    const float p3 = __fsub_rn(__fmul_rn(tau, __fadd_rn(__fmul_rn(tau, __fsub_rn(tau, 3.0f)), 6.0f)),
+                               __fmul_rn(6.0f, ev));
     const float w3 = (Q2 * (1.0f / 3.0f)) * (p3 * (rs2 * rs2));   // kernel.c:250-251
     const float flux_integral = fmaf(n1, rs2, fmaf(Q1, reuse, w3));
     tally = Geometry::weight * flux_integral;                      // kernel.c:262
