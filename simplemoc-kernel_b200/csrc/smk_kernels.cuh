@@ -116,7 +116,8 @@ attenuate_tracks(const KernelArgs a)
             for (int k = 0; k < count; ++k) {
                 const int qsr = (int)__shfl_sync(kFull, my_qsr, k, LPT);
                 const int fai = (int)__shfl_sync(kFull, my_fai, k, LPT);
-                const bool active = (b + k) < nseg;
+                // only the stream's ragged last track can be shorter than its warp-mates
+                const bool active = (LPT == 32) ? true : (b + k) < nseg;
                 const bool first = (fai == 0);
                 const bool last = (fai == F - 1);
                 const int64_t row = (int64_t)qsr * F + fai;
@@ -134,19 +135,22 @@ attenuate_tracks(const KernelArgs a)
                     const float4 st = ldg4(sig + c * LPT);
                     const float4 y1 = first ? zero : ldg4(src + c * LPT - row_f4);
                     const float4 y3 = last ? zero : ldg4(src + c * LPT + row_f4);
-                    float4 t;
+                    float4 t, ps = psi[c];
                     if constexpr (MATH == kMathFast) {
-                        attenuate_fast<EXPM>(fc, y1.x, y2.x, y3.x, st.x, s_pairs, psi[c].x, t.x);
-                        attenuate_fast<EXPM>(fc, y1.y, y2.y, y3.y, st.y, s_pairs, psi[c].y, t.y);
-                        attenuate_fast<EXPM>(fc, y1.z, y2.z, y3.z, st.z, s_pairs, psi[c].z, t.z);
-                        attenuate_fast<EXPM>(fc, y1.w, y2.w, y3.w, st.w, s_pairs, psi[c].w, t.w);
+                        attenuate_fast<EXPM>(fc, y1.x, y2.x, y3.x, st.x, s_pairs, ps.x, t.x);
+                        attenuate_fast<EXPM>(fc, y1.y, y2.y, y3.y, st.y, s_pairs, ps.y, t.y);
+                        attenuate_fast<EXPM>(fc, y1.z, y2.z, y3.z, st.z, s_pairs, ps.z, t.z);
+                        attenuate_fast<EXPM>(fc, y1.w, y2.w, y3.w, st.w, s_pairs, ps.w, t.w);
                     } else {
-                        attenuate_strict<EXPM>(first, last, y1.x, y2.x, y3.x, st.x, s_pairs, psi[c].x, t.x);
-                        attenuate_strict<EXPM>(first, last, y1.y, y2.y, y3.y, st.y, s_pairs, psi[c].y, t.y);
-                        attenuate_strict<EXPM>(first, last, y1.z, y2.z, y3.z, st.z, s_pairs, psi[c].z, t.z);
-                        attenuate_strict<EXPM>(first, last, y1.w, y2.w, y3.w, st.w, s_pairs, psi[c].w, t.w);
+                        attenuate_strict<EXPM>(first, last, y1.x, y2.x, y3.x, st.x, s_pairs, ps.x, t.x);
+                        attenuate_strict<EXPM>(first, last, y1.y, y2.y, y3.y, st.y, s_pairs, ps.y, t.y);
+                        attenuate_strict<EXPM>(first, last, y1.z, y2.z, y3.z, st.z, s_pairs, ps.z, t.z);
+                        attenuate_strict<EXPM>(first, last, y1.w, y2.w, y3.w, st.w, s_pairs, ps.w, t.w);
                     }
-                    if (active) red_add_v4(tal + c * LPT * 4, t.x, t.y, t.z, t.w);   // kernel.c:276
+                    if (active) {
+                        psi[c] = ps;                                              // kernel.c:331
+                        red_add_v4(tal + c * LPT * 4, t.x, t.y, t.z, t.w);        // kernel.c:276
+                    }
                 }
             }
         }
