@@ -25,7 +25,8 @@ import numpy as np
 from . import multi  # noqa: F401  (sharding + all-reduce plumbing)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsmk.so")
+# SMK_LIB selects an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("SMK_LIB") or os.path.join(HERE, "lib", "libsmk.so")
 
 EXP_POLY, EXP_MUFU, EXP_GLIBC, EXP_TABLE = 0, 1, 2, 3
 MATH_FAST, MATH_STRICT = 0, 1

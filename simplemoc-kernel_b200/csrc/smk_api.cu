@@ -171,8 +171,8 @@ static int validate(const smk_params *p, Shape &shape)
         return fail(SMK_EINVAL, "unknown math_mode %d", p->math_mode);
     if (!shape_for(p->egroups, shape))
         return fail(SMK_EINVAL, "egroups = %d unsupported (max 1024)", p->egroups);
-    if ((int64_t)p->source_3D_regions * p->fine_axial_intervals >= (1ll << 31))
-        return fail(SMK_EINVAL, "regions * intervals must be < 2^31");
+    if ((int64_t)p->source_3D_regions * p->fine_axial_intervals * (shape.groups_pad / 4) >= (1ll << 31))
+        return fail(SMK_EINVAL, "regions * intervals * padded groups / 4 must be < 2^31 (32-bit row offsets)");
     return SMK_OK;
 }
 

@@ -42,8 +42,13 @@ struct KernelArgs {
 };
 
 constexpr int kThreadsPerBlock = 256;
+#ifndef SMK_MIN_BLOCKS_FAST
+#define SMK_MIN_BLOCKS_FAST 4
+#endif
+// 4 x 256 threads x 64 registers = the whole register file: 32 warps/SM for the issue-bound FAST kernels
+constexpr int kMinBlocksFast = SMK_MIN_BLOCKS_FAST;
 
-__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
+__device__ __forceinline__ void red_add_v4(float4 *addr, float a, float b, float c, float d)
 {
     // one 16-byte vector reduction at L2 per lane (PTX ISA 8.1, sm_90+): SASS RED.E.ADD.F32x4
     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
@@ -57,8 +62,42 @@ __device__ __forceinline__ float4 ldg4(const float4 *p)
     return __ldg(p);
 }
 
+// One segment of one track, FAST arithmetic, for the NCHUNK float4 this lane owns: loads,
+// two packed (FP32x2) attenuations per float4, psi carry and the vector RED.
+template <int LPT, int NCHUNK, int EXPM, int FIT>
+__device__ __forceinline__ void segment_fast(const float4 *__restrict__ src, const float4 *__restrict__ sig,
+                                             float4 *tal, int row_f4, const FitCoeffs fc,
+                                             const float2 *s_pairs, float4 (&psi)[NCHUNK], bool active,
+                                             bool first = false, bool last = false)
+{
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 y2 = ldg4(src + c * LPT);
+        const float4 st = ldg4(sig + c * LPT);
+        float4 y1 = zero, y3 = zero;
+        if constexpr (FIT == kFitDynamic) {
+            if (!first) y1 = ldg4(src + c * LPT - row_f4);
+            if (!last) y3 = ldg4(src + c * LPT + row_f4);
+        } else {
+            if constexpr (FIT != kFitFirst) y1 = ldg4(src + c * LPT - row_f4);
+            if constexpr (FIT != kFitLast) y3 = ldg4(src + c * LPT + row_f4);
+        }
+        float2 p_lo = make_float2(psi[c].x, psi[c].y), p_hi = make_float2(psi[c].z, psi[c].w);
+        float2 t_lo, t_hi;
+        attenuate_fast2<EXPM, FIT>(fc, make_float2(y1.x, y1.y), make_float2(y2.x, y2.y), make_float2(y3.x, y3.y),
+                                   make_float2(st.x, st.y), s_pairs, p_lo, t_lo);
+        attenuate_fast2<EXPM, FIT>(fc, make_float2(y1.z, y1.w), make_float2(y2.z, y2.w), make_float2(y3.z, y3.w),
+                                   make_float2(st.z, st.w), s_pairs, p_hi, t_hi);
+        if (active) {
+            psi[c] = make_float4(p_lo.x, p_lo.y, p_hi.x, p_hi.y);                 // kernel.c:331
+            red_add_v4(tal + c * LPT, t_lo.x, t_lo.y, t_hi.x, t_hi.y);            // kernel.c:276
+        }
+    }
+}
+
 template <int LPT, int NCHUNK, int MATH, int EXPM>
-__global__ void __launch_bounds__(kThreadsPerBlock)
+__global__ void __launch_bounds__(kThreadsPerBlock, (NCHUNK == 1 && MATH == kMathFast) ? kMinBlocksFast : 1)
 attenuate_tracks(const KernelArgs a)
 {
     static_assert(LPT >= 1 && LPT <= 32 && (LPT & (LPT - 1)) == 0, "LPT must be a power of two");
@@ -114,42 +153,50 @@ attenuate_tracks(const KernelArgs a)
             }
             const int count = (nseg_warp - b) < LPT ? (nseg_warp - b) : LPT;
             for (int k = 0; k < count; ++k) {
-                const int qsr = (int)__shfl_sync(kFull, my_qsr, k, LPT);
-                const int fai = (int)__shfl_sync(kFull, my_fai, k, LPT);
+                const uint32_t qsr = __shfl_sync(kFull, my_qsr, k, LPT);
+                const uint32_t fai = __shfl_sync(kFull, my_fai, k, LPT);
                 // only the stream's ragged last track can be shorter than its warp-mates
                 const bool active = (LPT == 32) ? true : (b + k) < nseg;
-                const bool first = (fai == 0);
-                const bool last = (fai == F - 1);
-                const int64_t row = (int64_t)qsr * F + fai;
-                const float4 *src = a.source + row * row_f4 + sub;
-                const float4 *sig = a.sigT + (int64_t)qsr * row_f4 + sub;
-                float *tal = a.tally + (row * row_f4 + sub) * 4;
+                const bool first = (fai == 0u);
+                const bool last = (fai == (uint32_t)(F - 1));
+                // 32-bit row offsets (smk_create checks R * F * G_pad / 4 < 2^31)
+                const uint32_t row = qsr * (uint32_t)F + fai;
+                const uint32_t off = row * (uint32_t)row_f4 + (uint32_t)sub;
+                const float4 *src = a.source + off;
+                const float4 *sig = a.sigT + (qsr * (uint32_t)row_f4 + (uint32_t)sub);
+                float4 *tal = reinterpret_cast<float4 *>(a.tally) + off;
 
-                [[maybe_unused]] FitCoeffs fc;
-                if constexpr (MATH == kMathFast) fc = fit_coeffs(first, last);
-
+                if constexpr (MATH == kMathFast && LPT == 32) {
+                    // one track per warp: the segment type is warp-uniform, so branch on it and
+                    // run code specialised for the type (literal coefficients; the edge types
+                    // load 2 rows and skip the quadratic terms)
+                    if (first)
+                        segment_fast<LPT, NCHUNK, EXPM, kFitFirst>(src, sig, tal, row_f4, FitCoeffs{}, s_pairs, psi, true);
+                    else if (last)
+                        segment_fast<LPT, NCHUNK, EXPM, kFitLast>(src, sig, tal, row_f4, FitCoeffs{}, s_pairs, psi, true);
+                    else
+                        segment_fast<LPT, NCHUNK, EXPM, kFitInterior>(src, sig, tal, row_f4, FitCoeffs{}, s_pairs, psi, true);
+                } else if constexpr (MATH == kMathFast) {
+                    // several tracks per warp: types differ between lanes -> per-lane coefficients
+                    segment_fast<LPT, NCHUNK, EXPM, kFitDynamic>(src, sig, tal, row_f4, fit_coeffs(first, last),
+                                                                 s_pairs, psi, active, first, last);
+                } else {
 #pragma unroll
-                for (int c = 0; c < NCHUNK; ++c) {
-                    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 y2 = ldg4(src + c * LPT);
-                    const float4 st = ldg4(sig + c * LPT);
-                    const float4 y1 = first ? zero : ldg4(src + c * LPT - row_f4);
-                    const float4 y3 = last ? zero : ldg4(src + c * LPT + row_f4);
-                    float4 t, ps = psi[c];
-                    if constexpr (MATH == kMathFast) {
-                        attenuate_fast<EXPM>(fc, y1.x, y2.x, y3.x, st.x, s_pairs, ps.x, t.x);
-                        attenuate_fast<EXPM>(fc, y1.y, y2.y, y3.y, st.y, s_pairs, ps.y, t.y);
-                        attenuate_fast<EXPM>(fc, y1.z, y2.z, y3.z, st.z, s_pairs, ps.z, t.z);
-                        attenuate_fast<EXPM>(fc, y1.w, y2.w, y3.w, st.w, s_pairs, ps.w, t.w);
-                    } else {
+                    for (int c = 0; c < NCHUNK; ++c) {
+                        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 y2 = ldg4(src + c * LPT);
+                        const float4 st = ldg4(sig + c * LPT);
+                        const float4 y1 = first ? zero : ldg4(src + c * LPT - row_f4);
+                        const float4 y3 = last ? zero : ldg4(src + c * LPT + row_f4);
+                        float4 t, ps = psi[c];
                         attenuate_strict<EXPM>(first, last, y1.x, y2.x, y3.x, st.x, s_pairs, ps.x, t.x);
                         attenuate_strict<EXPM>(first, last, y1.y, y2.y, y3.y, st.y, s_pairs, ps.y, t.y);
                         attenuate_strict<EXPM>(first, last, y1.z, y2.z, y3.z, st.z, s_pairs, ps.z, t.z);
                         attenuate_strict<EXPM>(first, last, y1.w, y2.w, y3.w, st.w, s_pairs, ps.w, t.w);
-                    }
-                    if (active) {
-                        psi[c] = ps;                                              // kernel.c:331
-                        red_add_v4(tal + c * LPT * 4, t.x, t.y, t.z, t.w);        // kernel.c:276
+                        if (active) {
+                            psi[c] = ps;                                          // kernel.c:331
+                            red_add_v4(tal + c * LPT, t.x, t.y, t.z, t.w);        // kernel.c:276
+                        }
                     }
                 }
             }

@@ -218,6 +218,125 @@ __device__ __forceinline__ void attenuate_fast(const FitCoeffs &f, float y1, flo
     psi = fmaf(psi, e, acc);
 }
 
+// ------------------------------------------------------------------------------
+// FAST, packed: two intersections (two adjacent energy groups) per instruction with the
+// sm_100 FP32x2 datapath (PTX fma/mul/add.rn.f32x2, SASS FFMA2 / FMUL2 / FADD2).  Every
+// packed operation is the IEEE round-to-nearest operation on each half, so this is the
+// scalar FAST arithmetic with half the issue slots.  The kernel was issue-bound
+// (profiles/ncu_r01a_summary.md: issue active 80.7 %, FMA pipe 60 %).
+// ------------------------------------------------------------------------------
+__device__ __forceinline__ float2 f2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+// a - b with one rounding: fma(b, -1, a)
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, f2(-1.0f), a); }
+
+enum : int { kFitInterior = 0, kFitFirst = 1, kFitLast = 2, kFitDynamic = 3 };
+
+// the nine coefficients of fit_coeffs() as compile-time constants per segment type
+template <int FIT>
+struct FitConst {
+    static constexpr float dz = Geometry::dz, zin = Geometry::zin, mu = Geometry::mu, mu2 = Geometry::mu2;
+    static constexpr float k1 = 1.0f / (2.0f * dz), k2 = 1.0f / (2.0f * dz * dz), e = 1.0f / dz;
+    static constexpr bool first = FIT == kFitFirst, last = FIT == kFitLast;
+    static constexpr float a0 = first ? 0.0f : (last ? -e * zin : k1 * zin + k2 * zin * zin);
+    static constexpr float b0 = first ? 1.0f - e * zin : (last ? 1.0f + e * zin : 1.0f - 2.0f * k2 * zin * zin);
+    static constexpr float c0 = first ? e * zin : (last ? 0.0f : -k1 * zin + k2 * zin * zin);
+    static constexpr float a1 = first ? 0.0f : (last ? -mu * e : mu * (k1 + 2.0f * k2 * zin));
+    static constexpr float b1 = first ? -mu * e : (last ? mu * e : mu * (-4.0f * k2 * zin));
+    static constexpr float c1 = first ? mu * e : (last ? 0.0f : mu * (-k1 + 2.0f * k2 * zin));
+    static constexpr float a2 = (first || last) ? 0.0f : mu2 * k2;
+    static constexpr float b2 = (first || last) ? 0.0f : mu2 * -2.0f * k2;
+    static constexpr float c2 = (first || last) ? 0.0f : mu2 * k2;
+};
+
+// e = exp(-tau) on both halves; returns expVal = 1 - e
+template <int EXPM>
+__device__ __forceinline__ float2 exp_val2(float2 tau, float2 sigT, const float2 *s_pairs, float2 &e_out)
+{
+    if constexpr (EXPM == kExpPoly) {
+        const float2 x = mul2(sigT, f2(-Geometry::ds));             // -tau, exactly
+        float2 p = fma2(f2(0x1.415ffep-13f), x, f2(0x1.6336e4p-10f));
+        p = fma2(p, x, f2(0x1.10ac84p-7f));
+        p = fma2(p, x, f2(0x1.555146p-5f));
+        p = fma2(p, x, f2(0x1.555546p-3f));
+        p = fma2(p, x, f2(0.5f));
+        const float2 x2 = mul2(x, x);
+        const float2 s = add2(x, f2(1.0f));
+        const float2 lost = sub2(x, add2(s, f2(-1.0f)));            // exact: (1 + x) - s
+        const float2 e = add2(s, fma2(x2, p, lost));
+        e_out = e;
+        return sub2(f2(1.0f), e);
+    } else {
+        float ex, ey;
+        const float evx = exp_val<EXPM>(tau.x, s_pairs, ex);
+        const float evy = exp_val<EXPM>(tau.y, s_pairs, ey);
+        e_out = make_float2(ex, ey);
+        return make_float2(evx, evy);
+    }
+}
+
+// Two intersections.  FIT selects compile-time fit coefficients (edge types also skip the
+// quadratic terms, which are exactly zero there: q2 = 0, kernel.c:134,160) or, for
+// kFitDynamic, the per-lane coefficients in `f` (sub-warp tracks of different types).
+template <int EXPM, int FIT>
+__device__ __forceinline__ void attenuate_fast2(const FitCoeffs &f, float2 y1, float2 y2, float2 y3,
+                                                float2 sigT, const float2 *s_pairs, float2 &psi,
+                                                float2 &tally)
+{
+    constexpr bool kQuadratic = (FIT == kFitInterior) || (FIT == kFitDynamic);
+    float2 q0, Q1, Q2 = f2(0.0f);
+    if constexpr (FIT == kFitDynamic) {
+        q0 = fma2(f2(f.c0), y3, fma2(f2(f.b0), y2, mul2(f2(f.a0), y1)));
+        Q1 = fma2(f2(f.c1), y3, fma2(f2(f.b1), y2, mul2(f2(f.a1), y1)));
+        Q2 = fma2(f2(f.c2), y3, fma2(f2(f.b2), y2, mul2(f2(f.a2), y1)));
+    } else if constexpr (FIT == kFitInterior) {
+        using K = FitConst<kFitInterior>;
+        q0 = fma2(f2(K::c0), y3, fma2(f2(K::b0), y2, mul2(f2(K::a0), y1)));
+        Q1 = fma2(f2(K::c1), y3, fma2(f2(K::b1), y2, mul2(f2(K::a1), y1)));
+        Q2 = fma2(f2(K::c2), y3, fma2(f2(K::b2), y2, mul2(f2(K::a2), y1)));
+    } else if constexpr (FIT == kFitFirst) {
+        using K = FitConst<kFitFirst>;
+        q0 = fma2(f2(K::c0), y3, mul2(f2(K::b0), y2));
+        Q1 = fma2(f2(K::c1), y3, mul2(f2(K::b1), y2));
+    } else {
+        using K = FitConst<kFitLast>;
+        q0 = fma2(f2(K::a0), y1, mul2(f2(K::b0), y2));
+        Q1 = fma2(f2(K::a1), y1, mul2(f2(K::b1), y2));
+    }
+
+    const float2 tau = mul2(sigT, f2(Geometry::ds));
+    float2 e;
+    const float2 ev = exp_val2<EXPM>(tau, sigT, s_pairs, e);
+    const float2 tme = sub2(tau, ev);                               // tau - expVal (exact)
+
+    const float2 rs = make_float2(rcp_mufu(sigT.x), rcp_mufu(sigT.y));
+    const float2 rs2 = mul2(rs, rs);
+    // reuse = tau (tau - 2) + 2 expVal / sigT^3             (kernel.c:235-236)
+    const float2 reuse = fma2(f2(2.0f), mul2(ev, mul2(rs2, rs)), mul2(tau, add2(tau, f2(-2.0f))));
+    // q0 tau + (sigT psi - q0) expVal = q0 (tau - expVal) + sigT psi expVal   (kernel.c:248)
+    const float2 n1 = fma2(q0, tme, mul2(mul2(sigT, psi), ev));
+    float2 fi;
+    if constexpr (kQuadratic) {
+        // tau (tau (tau - 3) + 6) - 6 expVal in the reference's order (see attenuate_fast)
+        const float2 cubic = sub2(mul2(tau, add2(mul2(tau, add2(tau, f2(-3.0f))), f2(6.0f))),
+                                  mul2(f2(6.0f), ev));
+        const float2 w3 = mul2(mul2(Q2, f2(1.0f / 3.0f)), mul2(cubic, mul2(rs2, rs2)));
+        fi = fma2(Q1, reuse, w3);
+    } else {
+        fi = mul2(Q1, reuse);
+    }
+    fi = fma2(n1, rs2, fi);
+    tally = mul2(f2(Geometry::weight), fi);                         // kernel.c:262
+
+    // psi_out = t1 + t2 + t3 + t4                           (kernel.c:291-331)
+    float2 acc = mul2(mul2(q0, ev), rs);
+    acc = fma2(mul2(Q1, tme), rs2, acc);
+    if constexpr (kQuadratic) acc = fma2(Q2, reuse, acc);
+    psi = fma2(psi, e, acc);
+}
+
 // STRICT: one intersection in the reference's own operation order.
 template <int EXPM>
 __device__ __forceinline__ void attenuate_strict(bool first, bool last, float y1, float y2,
