@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -93,6 +94,9 @@ static bool shape_for(int groups, Shape &s)
 
 typedef void (*AttenuateFn)(const KernelArgs);
 
+// ring slots per warp of the TMA-staged kernel used by default where it exists (0 = direct loads)
+constexpr int kDefaultStages = 0;
+
 template <int LPT, int NCHUNK>
 static AttenuateFn pick_modes(int math, int expm)
 {
@@ -131,6 +135,53 @@ static AttenuateFn pick_kernel(const Shape &s, int math, int expm)
     return nullptr;
 }
 
+// TMA-staged variants exist for the one-track-per-warp shapes (LPT = 32), FAST math only.
+template <int NCHUNK, int STAGES>
+static AttenuateFn pick_staged_exp(int expm)
+{
+    switch (expm) {
+        case kExpPoly: return attenuate_tracks_staged<NCHUNK, kExpPoly, STAGES>;
+        case kExpMufu: return attenuate_tracks_staged<NCHUNK, kExpMufu, STAGES>;
+        case kExpGlibc: return attenuate_tracks_staged<NCHUNK, kExpGlibc, STAGES>;
+        case kExpTable: return attenuate_tracks_staged<NCHUNK, kExpTable, STAGES>;
+    }
+    return nullptr;
+}
+
+template <int NCHUNK, bool PREFETCH>
+static AttenuateFn pick_pf_exp(int expm)
+{
+    switch (expm) {
+        case kExpPoly: return attenuate_tracks_pf<NCHUNK, kExpPoly, PREFETCH>;
+        case kExpMufu: return attenuate_tracks_pf<NCHUNK, kExpMufu, PREFETCH>;
+        case kExpGlibc: return attenuate_tracks_pf<NCHUNK, kExpGlibc, PREFETCH>;
+        case kExpTable: return attenuate_tracks_pf<NCHUNK, kExpTable, PREFETCH>;
+    }
+    return nullptr;
+}
+
+// flat-loop kernels for the one-track-per-warp shapes, FAST math: "flat" (loads at use) and
+// "prefetch" (software-pipelined through a second register set)
+static AttenuateFn pick_flat(const Shape &s, int math, int expm, bool prefetch)
+{
+    if (math != kMathFast || s.lpt != 32) return nullptr;
+    if (prefetch) return s.nchunk == 1 ? pick_pf_exp<1, true>(expm) : nullptr;
+    switch (s.nchunk) {
+        case 1: return pick_pf_exp<1, false>(expm);
+    }
+    return nullptr;
+}
+
+static AttenuateFn pick_staged(const Shape &s, int math, int expm, int stages)
+{
+    if (math != kMathFast || s.lpt != 32 || s.nchunk != 1) return nullptr;
+    switch (stages) {
+        case 2: return pick_staged_exp<1, 2>(expm);
+        case 3: return pick_staged_exp<1, 3>(expm);
+    }
+    return nullptr;
+}
+
 }  // namespace smk
 
 using namespace smk;
@@ -139,6 +190,8 @@ struct smk_ctx {
     smk_params p;
     Shape shape;
     AttenuateFn kernel;
+    int stages;              // > 0: TMA-staged kernel with this many ring slots per warp
+    size_t dyn_smem;
     int sm_count;
     int blocks_per_sm;
     int64_t rows;            // R * F
@@ -232,6 +285,24 @@ int smk_create(const smk_params *p, smk_ctx **out)
     c->p = *p;
     c->shape = shape;
     c->kernel = pick_kernel(shape, p->math_mode, p->exp_mode);
+    // kernel-variant knob for tuning experiments: SMK_KERNEL=direct | flat | prefetch | staged2 | staged3
+    const char *variant = getenv("SMK_KERNEL");
+    int stages = kDefaultStages;
+    if (variant && strcmp(variant, "direct") == 0) stages = 0;
+    else if (variant && strncmp(variant, "staged", 6) == 0) stages = atoi(variant + 6);
+    if (variant && (strcmp(variant, "prefetch") == 0 || strcmp(variant, "flat") == 0)) {
+        AttenuateFn pf = pick_flat(shape, p->math_mode, p->exp_mode, strcmp(variant, "prefetch") == 0);
+        if (pf) c->kernel = pf;
+        stages = 0;
+    }
+    if (stages > 0) {
+        AttenuateFn staged = pick_staged(shape, p->math_mode, p->exp_mode, stages);
+        if (staged) {
+            c->kernel = staged;
+            c->stages = stages;
+            c->dyn_smem = (size_t)(kThreadsPerBlock / 32) * stages * 4 * shape.groups_pad * sizeof(float);
+        }
+    }
     if (!c->kernel) {
         delete c;
         return fail(SMK_EINVAL, "no kernel for egroups=%d math=%d exp=%d", p->egroups, p->math_mode,
@@ -243,8 +314,10 @@ int smk_create(const smk_params *p, smk_ctx **out)
     cudaDeviceProp prop;
     SMK_CUDA(cudaGetDeviceProperties(&prop, p->device));
     c->sm_count = prop.multiProcessorCount;
+    if (c->dyn_smem > 0)
+        SMK_CUDA(cudaFuncSetAttribute(c->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dyn_smem));
     SMK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->blocks_per_sm, c->kernel,
-                                                           kThreadsPerBlock, 0));
+                                                           kThreadsPerBlock, c->dyn_smem));
     if (c->blocks_per_sm < 1) c->blocks_per_sm = 1;
 
     ExpTable tab;
@@ -420,7 +493,7 @@ static int launch(smk_ctx *c, int64_t track_begin, int64_t track_end)
     int64_t want = (tracks + slots_per_block - 1) / slots_per_block;
     int64_t full = (int64_t)c->sm_count * c->blocks_per_sm;
     int grid = (int)(want < full ? want : full);
-    c->kernel<<<grid, kThreadsPerBlock, 0, c->stream>>>(a);
+    c->kernel<<<grid, kThreadsPerBlock, c->dyn_smem, c->stream>>>(a);
     SMK_CUDA(cudaGetLastError());
     c->launches += 1;
     return SMK_OK;

@@ -251,6 +251,16 @@ struct FitConst {
     static constexpr float c2 = (first || last) ? 0.0f : mu2 * k2;
 };
 
+// fit coefficients in difference form (one operation fewer than the y1/y2/y3 form)
+struct FitDiff {
+    static constexpr float dz = Geometry::dz, zin = Geometry::zin, mu = Geometry::mu, mu2 = Geometry::mu2;
+    static constexpr float k1 = 1.0f / (2.0f * dz), k2 = 1.0f / (2.0f * dz * dz);
+    static constexpr float q0_d = k1 * zin, q0_s = k2 * zin * zin;          // 1.5, 4.5
+    static constexpr float q1_d = mu * k1, q1_s = mu * 2.0f * k2 * zin;     // 4.5, 27
+    static constexpr float q2_s = mu2 * k2;                                 // 15
+    static constexpr float e0 = zin / dz, e1 = mu / dz;                     // 3, 9
+};
+
 // e = exp(-tau) on both halves; returns expVal = 1 - e
 template <int EXPM>
 __device__ __forceinline__ float2 exp_val2(float2 tau, float2 sigT, const float2 *s_pairs, float2 &e_out)
@@ -292,18 +302,21 @@ __device__ __forceinline__ void attenuate_fast2(const FitCoeffs &f, float2 y1, f
         Q1 = fma2(f2(f.c1), y3, fma2(f2(f.b1), y2, mul2(f2(f.a1), y1)));
         Q2 = fma2(f2(f.c2), y3, fma2(f2(f.b2), y2, mul2(f2(f.a2), y1)));
     } else if constexpr (FIT == kFitInterior) {
-        using K = FitConst<kFitInterior>;
-        q0 = fma2(f2(K::c0), y3, fma2(f2(K::b0), y2, mul2(f2(K::a0), y1)));
-        Q1 = fma2(f2(K::c1), y3, fma2(f2(K::b1), y2, mul2(f2(K::a1), y1)));
-        Q2 = fma2(f2(K::c2), y3, fma2(f2(K::b2), y2, mul2(f2(K::a2), y1)));
+        // d = y1 - y3, s = y1 - 2 y2 + y3:  c1 = d / (2 dz), c2 = s / (2 dz^2)   (kernel.c:182-184)
+        using K = FitDiff;
+        const float2 d = sub2(y1, y3);
+        const float2 s = fma2(y2, f2(-2.0f), add2(y1, y3));
+        q0 = fma2(f2(K::q0_s), s, fma2(f2(K::q0_d), d, y2));       // y2 + c1 zin + c2 zin^2
+        Q1 = fma2(f2(K::q1_s), s, mul2(f2(K::q1_d), d));           // mu (c1 + 2 c2 zin)
+        Q2 = mul2(f2(K::q2_s), s);                                 // mu2 c2
     } else if constexpr (FIT == kFitFirst) {
-        using K = FitConst<kFitFirst>;
-        q0 = fma2(f2(K::c0), y3, mul2(f2(K::b0), y2));
-        Q1 = fma2(f2(K::c1), y3, mul2(f2(K::b1), y2));
+        const float2 d = sub2(y3, y2);                             // c1 = (y3 - y2) / dz  (kernel.c:128)
+        q0 = fma2(f2(FitDiff::e0), d, y2);
+        Q1 = mul2(f2(FitDiff::e1), d);
     } else {
-        using K = FitConst<kFitLast>;
-        q0 = fma2(f2(K::a0), y1, mul2(f2(K::b0), y2));
-        Q1 = fma2(f2(K::a1), y1, mul2(f2(K::b1), y2));
+        const float2 d = sub2(y2, y1);                             // c1 = (y2 - y1) / dz  (kernel.c:154)
+        q0 = fma2(f2(FitDiff::e0), d, y2);
+        Q1 = mul2(f2(FitDiff::e1), d);
     }
 
     const float2 tau = mul2(sigT, f2(Geometry::ds));
