@@ -148,6 +148,35 @@ int64_t smk_padded_elems(const smk_ctx *ctx); /* R*F*G_pad                      
 void *smk_alloc_host(size_t bytes);
 void  smk_free_host(void *p);
 
+/* ---- multi-GPU sweep in one process (north star item 4) ----------------- */
+/*
+ * One context per device; the tracks of the stream are sharded by contiguous range
+ * (device k sweeps tracks [k*T/P, (k+1)*T/P)); every device holds a replica of the
+ * source data and its own zeroed tally deltas; ONE all-reduce of the tally arrays ends
+ * the sweep.  The reference has no multi-device path (only -d <id>, io.cu:148-158).
+ * all-reduce implementations:
+ *   SMK_ALLREDUCE_PEER  one kernel per device over NVLink peer memory: device k sums slice k
+ *                       of every peer's tallies (P2P loads) and writes the sum back to every
+ *                       peer (P2P stores); deterministic summation order
+ *   SMK_ALLREDUCE_NCCL  ncclAllReduce (libnccl.so.2 is dlopen'ed on first use)
+ */
+#define SMK_ALLREDUCE_PEER 0
+#define SMK_ALLREDUCE_NCCL 1
+typedef struct smk_multi smk_multi;
+/* devices == NULL means ordinals 0 .. n_devices-1; p->device is ignored */
+int   smk_multi_create(const smk_params *p, int n_devices, const int *devices, int allreduce,
+                       smk_multi **out);
+void  smk_multi_destroy(smk_multi *m);
+int   smk_multi_upload(smk_multi *m, const float *fine_source, const float *fine_flux, const float *sigT);
+int   smk_multi_fill_device(smk_multi *m, float sigt_floor);
+/* sweep all tracks + all-reduce.  kernel_seconds = slowest device's kernel (CUDA events),
+ * total_seconds = wall clock from first launch to the end of the all-reduce; either may be NULL */
+int   smk_multi_run(smk_multi *m, double *kernel_seconds, double *total_seconds);
+/* flux0 + all-reduced tallies, read from device `which` (every device holds the same sum) */
+int   smk_multi_download_flux(smk_multi *m, int which, float *fine_flux_out);
+int   smk_multi_download_checksum(smk_multi *m, uint64_t *checksum);   /* summed over devices */
+int   smk_multi_device_count(const smk_multi *m);
+
 /* ---- diagnostics ------------------------------------------------------- */
 /* d_out[i] = exp(-tau[i]) as evaluated by exp_mode (host arrays, n elements);
  * used to sweep the exponential against libm */

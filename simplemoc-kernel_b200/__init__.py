@@ -75,6 +75,9 @@ ABI_SYMBOLS = (
     "smk_synchronize", "smk_launch_count", "smk_run_host", "smk_device_tally",
     "smk_device_flux0", "smk_device_source", "smk_device_sigT", "smk_padded_elems",
     "smk_alloc_host", "smk_free_host", "smk_debug_exp", "smk_debug_segment_ids",
+    "smk_multi_create", "smk_multi_destroy", "smk_multi_upload", "smk_multi_fill_device",
+    "smk_multi_run", "smk_multi_download_flux", "smk_multi_download_checksum",
+    "smk_multi_device_count",
 )
 
 
@@ -118,6 +121,15 @@ def _load() -> C.CDLL:
     L.smk_alloc_host.restype = vp
     L.smk_free_host.argtypes = [vp]
     L.smk_free_host.restype = None
+    L.smk_multi_create.argtypes = [C.POINTER(Params), i32, C.POINTER(C.c_int), i32, C.POINTER(vp)]
+    L.smk_multi_destroy.argtypes = [vp]
+    L.smk_multi_destroy.restype = None
+    L.smk_multi_upload.argtypes = [vp, vp, vp, vp]
+    L.smk_multi_fill_device.argtypes = [vp, C.c_float]
+    L.smk_multi_run.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.smk_multi_download_flux.argtypes = [vp, i32, vp]
+    L.smk_multi_download_checksum.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.smk_multi_device_count.argtypes = [vp]
     L.smk_debug_exp.argtypes = [i32, _f32p, _f32p, i64, i32]
     L.smk_debug_segment_ids.argtypes = [C.POINTER(Params), i64, i64, _i32p, _i32p]
     return L
@@ -269,6 +281,53 @@ class Context:
     @property
     def padded_elems(self) -> int:
         return lib.smk_padded_elems(self._h)
+
+
+class MultiContext:
+    """One process, several GPUs: tracks sharded by range, one all-reduce of the tally deltas
+    (allreduce = "peer": NVLink peer-memory kernel, "nccl": ncclAllReduce)."""
+
+    def __init__(self, I: Input, n_devices: int, allreduce: str = "peer", devices=None):
+        self.I = I
+        self.p = I.params()
+        self._h = C.c_void_p()
+        ids = (C.c_int * n_devices)(*devices) if devices else None
+        _check(lib.smk_multi_create(C.byref(self.p), n_devices, ids, {"peer": 0, "nccl": 1}[allreduce],
+                                    C.byref(self._h)))
+        self.R, self.F, self.G = self.p.source_3D_regions, self.p.fine_axial_intervals, self.p.egroups
+
+    def close(self):
+        if self._h:
+            lib.smk_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def upload(self, fine_source, fine_flux, sigT):
+        _check(lib.smk_multi_upload(self._h, Context._ptr(fine_source), Context._ptr(fine_flux), Context._ptr(sigT)))
+
+    def fill_device(self, sigt_floor: float = 0.0):
+        _check(lib.smk_multi_fill_device(self._h, sigt_floor))
+
+    def run(self):
+        """Returns (slowest kernel seconds, wall seconds including the all-reduce)."""
+        ks, ts = C.c_double(0.0), C.c_double(0.0)
+        _check(lib.smk_multi_run(self._h, C.byref(ks), C.byref(ts)))
+        return ks.value, ts.value
+
+    def download_flux(self, which: int = 0):
+        out = np.empty((self.R, self.F, self.G), np.float32)
+        _check(lib.smk_multi_download_flux(self._h, which, out.ctypes.data))
+        return out
+
+    def checksum(self) -> int:
+        v = C.c_uint64(0)
+        _check(lib.smk_multi_download_checksum(self._h, C.byref(v)))
+        return v.value
 
 
 def run_kernel(I: Input, fine_source: np.ndarray, fine_flux: np.ndarray, sigT: np.ndarray):

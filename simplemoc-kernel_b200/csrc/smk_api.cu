@@ -4,7 +4,9 @@
 // picks the kernel instantiation for (G, math mode, exp mode) and sizes the grid as
 // a multiple of the SM count (persistent CTAs striding over tracks).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -94,8 +96,6 @@ static bool shape_for(int groups, Shape &s)
 
 typedef void (*AttenuateFn)(const KernelArgs);
 
-// ring slots per warp of the TMA-staged kernel used by default where it exists (0 = direct loads)
-constexpr int kDefaultStages = 0;
 
 template <int LPT, int NCHUNK>
 static AttenuateFn pick_modes(int math, int expm)
@@ -148,23 +148,24 @@ static AttenuateFn pick_staged_exp(int expm)
     return nullptr;
 }
 
-template <int NCHUNK, bool PREFETCH>
+template <int NCHUNK, bool PREFETCH, bool DEFER = false>
 static AttenuateFn pick_pf_exp(int expm)
 {
     switch (expm) {
-        case kExpPoly: return attenuate_tracks_pf<NCHUNK, kExpPoly, PREFETCH>;
-        case kExpMufu: return attenuate_tracks_pf<NCHUNK, kExpMufu, PREFETCH>;
-        case kExpGlibc: return attenuate_tracks_pf<NCHUNK, kExpGlibc, PREFETCH>;
-        case kExpTable: return attenuate_tracks_pf<NCHUNK, kExpTable, PREFETCH>;
+        case kExpPoly: return attenuate_tracks_pf<NCHUNK, kExpPoly, PREFETCH, DEFER>;
+        case kExpMufu: return attenuate_tracks_pf<NCHUNK, kExpMufu, PREFETCH, DEFER>;
+        case kExpGlibc: return attenuate_tracks_pf<NCHUNK, kExpGlibc, PREFETCH, DEFER>;
+        case kExpTable: return attenuate_tracks_pf<NCHUNK, kExpTable, PREFETCH, DEFER>;
     }
     return nullptr;
 }
 
 // flat-loop kernels for the one-track-per-warp shapes, FAST math: "flat" (loads at use) and
 // "prefetch" (software-pipelined through a second register set)
-static AttenuateFn pick_flat(const Shape &s, int math, int expm, bool prefetch)
+static AttenuateFn pick_flat(const Shape &s, int math, int expm, bool prefetch, bool defer = false)
 {
     if (math != kMathFast || s.lpt != 32) return nullptr;
+    if (defer) return s.nchunk == 1 ? pick_pf_exp<1, false, true>(expm) : nullptr;
     if (prefetch) return s.nchunk == 1 ? pick_pf_exp<1, true>(expm) : nullptr;
     switch (s.nchunk) {
         case 1: return pick_pf_exp<1, false>(expm);
@@ -285,23 +286,26 @@ int smk_create(const smk_params *p, smk_ctx **out)
     c->p = *p;
     c->shape = shape;
     c->kernel = pick_kernel(shape, p->math_mode, p->exp_mode);
-    // kernel-variant knob for tuning experiments: SMK_KERNEL=direct | flat | prefetch | staged2 | staged3
+    // Kernel variants.  Default: the flat-loop kernel where it exists (one track per warp, FAST
+    // math), else the general kernel.  SMK_KERNEL = direct | flat | defer | prefetch | staged2 |
+    // staged3 selects another variant for the tuning experiments recorded in DESIGN.md section 5.3.
     const char *variant = getenv("SMK_KERNEL");
-    int stages = kDefaultStages;
-    if (variant && strcmp(variant, "direct") == 0) stages = 0;
-    else if (variant && strncmp(variant, "staged", 6) == 0) stages = atoi(variant + 6);
-    if (variant && (strcmp(variant, "prefetch") == 0 || strcmp(variant, "flat") == 0)) {
-        AttenuateFn pf = pick_flat(shape, p->math_mode, p->exp_mode, strcmp(variant, "prefetch") == 0);
+    if (!variant || !*variant) variant = "flat";
+    if (strcmp(variant, "flat") == 0 || strcmp(variant, "prefetch") == 0 || strcmp(variant, "defer") == 0) {
+        AttenuateFn pf = pick_flat(shape, p->math_mode, p->exp_mode, strcmp(variant, "prefetch") == 0,
+                                   strcmp(variant, "defer") == 0);
         if (pf) c->kernel = pf;
-        stages = 0;
-    }
-    if (stages > 0) {
+    } else if (strncmp(variant, "staged", 6) == 0) {
+        const int stages = atoi(variant + 6);
         AttenuateFn staged = pick_staged(shape, p->math_mode, p->exp_mode, stages);
         if (staged) {
             c->kernel = staged;
             c->stages = stages;
             c->dyn_smem = (size_t)(kThreadsPerBlock / 32) * stages * 4 * shape.groups_pad * sizeof(float);
         }
+    } else if (strcmp(variant, "direct") != 0) {
+        delete c;
+        return fail(SMK_EINVAL, "unknown SMK_KERNEL variant '%s'", variant);
     }
     if (!c->kernel) {
         delete c;
@@ -593,6 +597,245 @@ int smk_run_host(const smk_params *p, const float *fine_source, float *fine_flux
     cudaEventDestroy(t1);
     smk_destroy(c);
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------
+// multi-GPU, one process
+// ---------------------------------------------------------------------------------------
+namespace {
+// the few NCCL entry points we need, resolved from libnccl.so.2 at first use (no link-time
+// dependency: the peer-memory all-reduce needs no library at all)
+struct Nccl {
+    void *lib = nullptr;
+    int (*CommInitAll)(void **, int, const int *) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load()
+    {
+        if (lib) return true;
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return false;
+        CommInitAll = (int (*)(void **, int, const int *))dlsym(lib, "ncclCommInitAll");
+        CommDestroy = (int (*)(void *))dlsym(lib, "ncclCommDestroy");
+        GroupStart = (int (*)())dlsym(lib, "ncclGroupStart");
+        GroupEnd = (int (*)())dlsym(lib, "ncclGroupEnd");
+        AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(lib, "ncclAllReduce");
+        GetErrorString = (const char *(*)(int))dlsym(lib, "ncclGetErrorString");
+        return CommInitAll && CommDestroy && GroupStart && GroupEnd && AllReduce;
+    }
+};
+Nccl g_nccl;
+constexpr int kNcclFloat32 = 7, kNcclSum = 0;   // ncclFloat32, ncclSum (nccl.h)
+}  // namespace
+
+struct smk_multi {
+    int n;
+    int allreduce;
+    smk_ctx *ctx[kMaxDevices];
+    cudaEvent_t start[kMaxDevices], swept[kMaxDevices], reduced[kMaxDevices];
+    void *comms[kMaxDevices];
+    bool have_comms;
+};
+
+int smk_multi_device_count(const smk_multi *m) { return m ? m->n : 0; }
+
+void smk_multi_destroy(smk_multi *m)
+{
+    if (!m) return;
+    for (int d = 0; d < m->n; ++d) {
+        if (!m->ctx[d]) continue;
+        cudaSetDevice(m->ctx[d]->p.device);
+        if (m->have_comms && m->comms[d]) g_nccl.CommDestroy(m->comms[d]);
+        if (m->start[d]) cudaEventDestroy(m->start[d]);
+        if (m->swept[d]) cudaEventDestroy(m->swept[d]);
+        if (m->reduced[d]) cudaEventDestroy(m->reduced[d]);
+        smk_destroy(m->ctx[d]);
+    }
+    delete m;
+}
+
+int smk_multi_create(const smk_params *p, int n_devices, const int *devices, int allreduce, smk_multi **out)
+{
+    if (!out) return fail(SMK_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!p) return fail(SMK_EINVAL, "params is NULL");
+    if (n_devices < 1 || n_devices > kMaxDevices) return fail(SMK_EINVAL, "n_devices must be in [1, %d]", kMaxDevices);
+    if (allreduce != SMK_ALLREDUCE_PEER && allreduce != SMK_ALLREDUCE_NCCL)
+        return fail(SMK_EINVAL, "unknown all-reduce implementation %d", allreduce);
+    int visible = 0;
+    SMK_CUDA(cudaGetDeviceCount(&visible));
+    smk_multi *m = new (std::nothrow) smk_multi();
+    if (!m) return fail(SMK_ENOMEM, "out of host memory");
+    memset(m, 0, sizeof(*m));
+    m->n = n_devices;
+    m->allreduce = allreduce;
+    int ids[kMaxDevices];
+    for (int d = 0; d < n_devices; ++d) {
+        ids[d] = devices ? devices[d] : d;
+        if (ids[d] < 0 || ids[d] >= visible) {
+            smk_multi_destroy(m);
+            return fail(SMK_EINVAL, "device %d out of range (%d visible)", ids[d], visible);
+        }
+    }
+    for (int d = 0; d < n_devices; ++d) {
+        smk_params pd = *p;
+        pd.device = ids[d];
+        int rc = smk_create(&pd, &m->ctx[d]);
+        if (rc != SMK_OK) {
+            smk_multi_destroy(m);
+            return rc;
+        }
+        cudaEventCreate(&m->start[d]);
+        cudaEventCreate(&m->swept[d]);
+        cudaEventCreateWithFlags(&m->reduced[d], cudaEventDisableTiming);
+    }
+    if (n_devices > 1 && allreduce == SMK_ALLREDUCE_PEER) {
+        for (int d = 0; d < n_devices; ++d) {
+            cudaSetDevice(ids[d]);
+            for (int e = 0; e < n_devices; ++e) {
+                if (e == d) continue;
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, ids[d], ids[e]);
+                if (!can) {
+                    smk_multi_destroy(m);
+                    return fail(SMK_ECUDA, "device %d cannot access peer %d (no NVLink/P2P path)", ids[d], ids[e]);
+                }
+                cudaError_t err = cudaDeviceEnablePeerAccess(ids[e], 0);
+                if (err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled) {
+                    smk_multi_destroy(m);
+                    return fail(SMK_ECUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", ids[d], ids[e], cudaGetErrorString(err));
+                }
+                cudaGetLastError();
+            }
+        }
+    }
+    if (n_devices > 1 && allreduce == SMK_ALLREDUCE_NCCL) {
+        if (!g_nccl.load()) {
+            smk_multi_destroy(m);
+            return fail(SMK_ESTATE, "libnccl.so.2 could not be loaded: %s", dlerror());
+        }
+        int rc = g_nccl.CommInitAll(m->comms, n_devices, ids);
+        if (rc != 0) {
+            smk_multi_destroy(m);
+            return fail(SMK_ECUDA, "ncclCommInitAll: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+        }
+        m->have_comms = true;
+    }
+    *out = m;
+    return SMK_OK;
+}
+
+int smk_multi_upload(smk_multi *m, const float *fine_source, const float *fine_flux, const float *sigT)
+{
+    if (!m) return fail(SMK_EINVAL, "multi is NULL");
+    for (int d = 0; d < m->n; ++d) {
+        int rc = smk_upload(m->ctx[d], fine_source, fine_flux, sigT);
+        if (rc != SMK_OK) return rc;
+    }
+    return SMK_OK;
+}
+
+int smk_multi_fill_device(smk_multi *m, float sigt_floor)
+{
+    if (!m) return fail(SMK_EINVAL, "multi is NULL");
+    for (int d = 0; d < m->n; ++d) {
+        int rc = smk_fill_device(m->ctx[d], sigt_floor);
+        if (rc != SMK_OK) return rc;
+    }
+    return SMK_OK;
+}
+
+int smk_multi_run(smk_multi *m, double *kernel_seconds, double *total_seconds)
+{
+    if (!m) return fail(SMK_EINVAL, "multi is NULL");
+    const int P = m->n;
+    const int64_t T = m->ctx[0]->n_tracks;
+    for (int d = 0; d < P; ++d) {
+        int rc = smk_reset_tallies(m->ctx[d]);
+        if (rc != SMK_OK) return rc;
+    }
+    for (int d = 0; d < P; ++d) SMK_CUDA(cudaStreamSynchronize(m->ctx[d]->stream));
+    const auto t0 = std::chrono::steady_clock::now();
+
+    // 1. the sweep: device d takes tracks [d*T/P, (d+1)*T/P)
+    for (int d = 0; d < P; ++d) {
+        smk_ctx *c = m->ctx[d];
+        SMK_CUDA(cudaSetDevice(c->p.device));
+        SMK_CUDA(cudaEventRecord(m->start[d], c->stream));
+        int rc = launch(c, d * T / P, (d + 1) * T / P);
+        if (rc != SMK_OK) return rc;
+        SMK_CUDA(cudaEventRecord(m->swept[d], c->stream));
+    }
+    // 2. one all-reduce of the tally deltas
+    if (P > 1 && m->allreduce == SMK_ALLREDUCE_PEER) {
+        PeerArrays arrays;
+        for (int d = 0; d < kMaxDevices; ++d) arrays.p[d] = d < P ? reinterpret_cast<float4 *>(m->ctx[d]->d_tally) : nullptr;
+        const int64_t n4 = m->ctx[0]->rows * m->ctx[0]->shape.groups_pad / 4;
+        for (int d = 0; d < P; ++d) {
+            smk_ctx *c = m->ctx[d];
+            SMK_CUDA(cudaSetDevice(c->p.device));
+            for (int e = 0; e < P; ++e)
+                if (e != d) SMK_CUDA(cudaStreamWaitEvent(c->stream, m->swept[e], 0));
+            const int64_t b = d * n4 / P, e4 = (d + 1) * n4 / P;
+            allreduce_peer_slices<<<layout_grid(e4 - b), 256, 0, c->stream>>>(arrays, P, b, e4);
+            SMK_CUDA(cudaGetLastError());
+            c->launches += 1;
+            SMK_CUDA(cudaEventRecord(m->reduced[d], c->stream));
+        }
+        for (int d = 0; d < P; ++d) {       // nobody reads its tallies before every slice is written
+            SMK_CUDA(cudaSetDevice(m->ctx[d]->p.device));
+            for (int e = 0; e < P; ++e)
+                if (e != d) SMK_CUDA(cudaStreamWaitEvent(m->ctx[d]->stream, m->reduced[e], 0));
+        }
+    } else if (P > 1) {
+        const size_t n = (size_t)(m->ctx[0]->rows * m->ctx[0]->shape.groups_pad);
+        int rc = g_nccl.GroupStart();
+        for (int d = 0; d < P && rc == 0; ++d)
+            rc = g_nccl.AllReduce(m->ctx[d]->d_tally, m->ctx[d]->d_tally, n, kNcclFloat32, kNcclSum, m->comms[d],
+                                  m->ctx[d]->stream);
+        if (rc == 0) rc = g_nccl.GroupEnd();
+        if (rc != 0) return fail(SMK_ECUDA, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    }
+    for (int d = 0; d < P; ++d) {
+        SMK_CUDA(cudaSetDevice(m->ctx[d]->p.device));
+        SMK_CUDA(cudaStreamSynchronize(m->ctx[d]->stream));
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    if (total_seconds) *total_seconds = std::chrono::duration<double>(t1 - t0).count();
+    if (kernel_seconds) {
+        double worst = 0.0;
+        for (int d = 0; d < P; ++d) {
+            float ms = 0.f;
+            SMK_CUDA(cudaSetDevice(m->ctx[d]->p.device));
+            SMK_CUDA(cudaEventElapsedTime(&ms, m->start[d], m->swept[d]));
+            if (ms * 1e-3 > worst) worst = ms * 1e-3;
+        }
+        *kernel_seconds = worst;
+    }
+    return SMK_OK;
+}
+
+int smk_multi_download_flux(smk_multi *m, int which, float *out)
+{
+    if (!m || which < 0 || which >= m->n) return fail(SMK_EINVAL, "bad device index");
+    return smk_download_flux(m->ctx[which], out);
+}
+
+int smk_multi_download_checksum(smk_multi *m, uint64_t *checksum)
+{
+    if (!m || !checksum) return fail(SMK_EINVAL, "NULL argument");
+    uint64_t sum = 0;
+    for (int d = 0; d < m->n; ++d) {
+        uint64_t v = 0;
+        int rc = smk_download_checksum(m->ctx[d], &v);
+        if (rc != SMK_OK) return rc;
+        sum += v;
+    }
+    *checksum = sum;
+    return SMK_OK;
 }
 
 void *smk_device_tally(smk_ctx *c) { return c ? c->d_tally : nullptr; }

@@ -464,8 +464,8 @@ __device__ __forceinline__ void load_rows(SegRows<NCHUNK> &r, const float4 *__re
 }
 
 template <int NCHUNK, int EXPM, int FIT>
-__device__ __forceinline__ void compute_rows(const SegRows<NCHUNK> &r, float4 *tal, const float2 *s_pairs,
-                                             float4 (&psi)[NCHUNK])
+__device__ __forceinline__ void compute_rows(const SegRows<NCHUNK> &r, const float2 *s_pairs, float4 (&psi)[NCHUNK],
+                                             float4 (&tally)[NCHUNK])
 {
 #pragma unroll
     for (int c = 0; c < NCHUNK; ++c) {
@@ -478,24 +478,33 @@ __device__ __forceinline__ void compute_rows(const SegRows<NCHUNK> &r, float4 *t
                                    make_float2(r.y3[c].z, r.y3[c].w), make_float2(r.st[c].z, r.st[c].w), s_pairs,
                                    p_hi, t_hi);
         psi[c] = make_float4(p_lo.x, p_lo.y, p_hi.x, p_hi.y);                     // kernel.c:331
-        red_add_v4(tal + c * 32, t_lo.x, t_lo.y, t_hi.x, t_hi.y);                 // kernel.c:276
+        tally[c] = make_float4(t_lo.x, t_lo.y, t_hi.x, t_hi.y);
     }
 }
 
+// attenuation of one segment by its (warp-uniform) type; the tally comes back in registers
 template <int NCHUNK, int EXPM>
-__device__ __forceinline__ void compute_by_type(const SegRows<NCHUNK> &r, uint32_t packed, float *tally, int lane,
-                                                const float2 *s_pairs, float4 (&psi)[NCHUNK])
+__device__ __forceinline__ void compute_by_type(const SegRows<NCHUNK> &r, uint32_t packed, const float2 *s_pairs,
+                                                float4 (&psi)[NCHUNK], float4 (&tally)[NCHUNK])
 {
-    float4 *tal = reinterpret_cast<float4 *>(tally) + ((packed & kRowMask) * (uint32_t)(32 * NCHUNK) + (uint32_t)lane);
     if (packed & kFlagFirst)
-        compute_rows<NCHUNK, EXPM, kFitFirst>(r, tal, s_pairs, psi);
+        compute_rows<NCHUNK, EXPM, kFitFirst>(r, s_pairs, psi, tally);
     else if (packed & kFlagLast)
-        compute_rows<NCHUNK, EXPM, kFitLast>(r, tal, s_pairs, psi);
+        compute_rows<NCHUNK, EXPM, kFitLast>(r, s_pairs, psi, tally);
     else
-        compute_rows<NCHUNK, EXPM, kFitInterior>(r, tal, s_pairs, psi);
+        compute_rows<NCHUNK, EXPM, kFitInterior>(r, s_pairs, psi, tally);
 }
 
-template <int NCHUNK, int EXPM, bool PREFETCH>
+// FSR_flux[g] += tally[g] (kernel.c:276) for the row of `packed`: one vector RED per lane
+template <int NCHUNK>
+__device__ __forceinline__ void red_row(float *tally_base, uint32_t packed, int lane, const float4 (&t)[NCHUNK])
+{
+    float4 *tal = reinterpret_cast<float4 *>(tally_base) + ((packed & kRowMask) * (uint32_t)(32 * NCHUNK) + (uint32_t)lane);
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) red_add_v4(tal + c * 32, t[c].x, t[c].y, t[c].z, t[c].w);
+}
+
+template <int NCHUNK, int EXPM, bool PREFETCH, bool DEFER>
 __global__ void __launch_bounds__(kThreadsPerBlock, (NCHUNK == 1) ? (PREFETCH ? kMinBlocksPrefetch : kMinBlocksFast) : 1)
 attenuate_tracks_pf(const KernelArgs a)
 {
@@ -558,6 +567,7 @@ attenuate_tracks_pf(const KernelArgs a)
             }
         };
 
+        float4 t[NCHUNK];
         if constexpr (PREFETCH) {
             SegRows<NCHUNK> ra, rb;
             uint32_t pa, qa, pb = 0u, qb = 0u;
@@ -568,23 +578,41 @@ attenuate_tracks_pf(const KernelArgs a)
                     ids_of(s + 1, s, pb, qb);
                     load_rows<NCHUNK>(rb, a.source, a.sigT, pb, qb, lane);
                 }
-                compute_by_type<NCHUNK, EXPM>(ra, pa, a.tally, lane, s_pairs, psi);
+                compute_by_type<NCHUNK, EXPM>(ra, pa, s_pairs, psi, t);
+                red_row<NCHUNK>(a.tally, pa, lane, t);
                 rotate(s);
                 if (s + 1 >= nseg) break;
                 if (s + 2 < nseg) {                                   // request s+2, compute s+1
                     ids_of(s + 2, s + 1, pa, qa);
                     load_rows<NCHUNK>(ra, a.source, a.sigT, pa, qa, lane);
                 }
-                compute_by_type<NCHUNK, EXPM>(rb, pb, a.tally, lane, s_pairs, psi);
+                compute_by_type<NCHUNK, EXPM>(rb, pb, s_pairs, psi, t);
+                red_row<NCHUNK>(a.tally, pb, lane, t);
                 rotate(s + 1);
             }
+        } else if constexpr (DEFER) {
+            // the RED of segment s-1 is issued right after the loads of segment s, i.e. while the
+            // warp would be waiting for those loads anyway
+            uint32_t pend = 0u;
+            for (int s = 0; s < nseg; ++s) {
+                SegRows<NCHUNK> r;
+                const uint32_t pk = __shfl_sync(kFull, cur_packed, s & 31);
+                const uint32_t qs = __shfl_sync(kFull, cur_qsr, s & 31);
+                load_rows<NCHUNK>(r, a.source, a.sigT, pk, qs, lane);
+                if (s > 0) red_row<NCHUNK>(a.tally, pend, lane, t);
+                compute_by_type<NCHUNK, EXPM>(r, pk, s_pairs, psi, t);
+                pend = pk;
+                rotate(s);
+            }
+            if (nseg > 0) red_row<NCHUNK>(a.tally, pend, lane, t);
         } else {
             for (int s = 0; s < nseg; ++s) {
                 SegRows<NCHUNK> r;
                 const uint32_t pk = __shfl_sync(kFull, cur_packed, s & 31);
                 const uint32_t qs = __shfl_sync(kFull, cur_qsr, s & 31);
                 load_rows<NCHUNK>(r, a.source, a.sigT, pk, qs, lane);
-                compute_by_type<NCHUNK, EXPM>(r, pk, a.tally, lane, s_pairs, psi);
+                compute_by_type<NCHUNK, EXPM>(r, pk, s_pairs, psi, t);
+                red_row<NCHUNK>(a.tally, pk, lane, t);
                 rotate(s);
             }
         }
@@ -652,6 +680,29 @@ __global__ void fill_rows(float *__restrict__ dst, int64_t rows, int groups, int
             v = (floor_ > 0.0f) ? __fadd_rn(floor_, __fmul_rn(u, span)) : u;
         }
         dst[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------
+// all-reduce of the tally deltas over NVLink peer memory (one launch per device):
+// this device sums float4 [begin, end) of every peer's array (P2P loads, fixed order so
+// that every device computes bit-identical sums) and writes the sum back to every peer.
+// ------------------------------------------------------------------------------
+constexpr int kMaxDevices = 8;
+struct PeerArrays {
+    float4 *p[kMaxDevices];
+};
+
+__global__ void allreduce_peer_slices(PeerArrays arrays, int n_dev, int64_t begin, int64_t end)
+{
+    for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float4 acc = arrays.p[0][i];
+        for (int d = 1; d < n_dev; ++d) {
+            const float4 v = arrays.p[d][i];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        for (int d = 0; d < n_dev; ++d) arrays.p[d][i] = acc;
     }
 }
 

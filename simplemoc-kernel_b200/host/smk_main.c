@@ -35,7 +35,7 @@ typedef struct {
     size_t nbytes;
     /* changed subsystems */
     unsigned long long seed;
-    int exp_mode, math_mode, device, gpus;
+    int exp_mode, math_mode, device, gpus, allreduce;
     int host_fill;
     float sigt_floor;
     const char *dump_flux;
@@ -104,6 +104,8 @@ static void usage_and_exit(void)
     puts("  --seed <n>            Seed of the counter-based segment stream (default 42)");
     puts("  --exp <mode>          poly | mufu | glibc | table (default poly)");
     puts("  --math <mode>         fast | strict (default fast)");
+    puts("  --gpus <n>            Split the segments over n GPUs, all-reduce the tallies");
+    puts("  --allreduce <impl>    peer (NVLink peer-memory kernel, default) | nccl");
     puts("  --host-fill           Fill the slabs on the host and upload them");
     puts("  --sigt-floor <x>      Well-conditioned diagnostic data: sigT in [x, 1)");
     puts("  --dump-flux <file>    Write the final scalar flux (raw float32)");
@@ -146,6 +148,7 @@ static void parse(int argc, char **argv, Input *I)
 {
     static const char *const exps[] = {"poly", "mufu", "glibc", "table"};
     static const char *const maths[] = {"fast", "strict"};
+    static const char *const reduces[] = {"peer", "nccl"};
     for (int i = 1; i < argc; i++) {
         const char *a = argv[i];
         if (!strcmp(a, "-t")) I->nthreads = atoi(need(argc, argv, &i));
@@ -157,12 +160,15 @@ static void parse(int argc, char **argv, Input *I)
         else if (!strcmp(a, "--seed")) I->seed = strtoull(need(argc, argv, &i), NULL, 10);
         else if (!strcmp(a, "--exp")) I->exp_mode = lookup(need(argc, argv, &i), exps, 4);
         else if (!strcmp(a, "--math")) I->math_mode = lookup(need(argc, argv, &i), maths, 2);
+        else if (!strcmp(a, "--gpus")) I->gpus = atoi(need(argc, argv, &i));
+        else if (!strcmp(a, "--allreduce")) I->allreduce = lookup(need(argc, argv, &i), reduces, 2);
         else if (!strcmp(a, "--host-fill")) I->host_fill = 1;
         else if (!strcmp(a, "--sigt-floor")) I->sigt_floor = (float)atof(need(argc, argv, &i));
         else if (!strcmp(a, "--dump-flux")) I->dump_flux = need(argc, argv, &i);
         else usage_and_exit();
     }
-    if (I->nthreads < 1 || I->segments < 0 || I->egroups < 1 || I->seg_per_thread < 1) usage_and_exit();
+    if (I->nthreads < 1 || I->segments < 0 || I->egroups < 1 || I->seg_per_thread < 1 || I->gpus < 1)
+        usage_and_exit();
 }
 
 static double estimate_mb(const Input *I)
@@ -189,6 +195,8 @@ static void summary(const Input *I, const char *device_name)
     printf("%-25s%d\n", "Segments per CUDA block:", I->seg_per_thread);
     printf("%-25s%s\n", "Exponential Table:", I->exp_mode == SMK_EXP_TABLE ? "ON" : "OFF");
     printf("%-25s%llu\n", "Stream Seed:", I->seed);
+    if (I->gpus > 1)
+        printf("%-25s%d (%s all-reduce)\n", "GPUs:", I->gpus, I->allreduce == SMK_ALLREDUCE_NCCL ? "NCCL" : "peer-memory");
     rule();
 }
 
@@ -261,7 +269,9 @@ int main(int argc, char *argv[])
     p.device = I.device;
 
     smk_ctx *ctx = NULL;
-    CHECK(smk_create(&p, &ctx));
+    smk_multi *multi = NULL;
+    if (I.gpus > 1) CHECK(smk_multi_create(&p, I.gpus, NULL, I.allreduce, &multi));
+    else CHECK(smk_create(&p, &ctx));
     const long n_fine = (long)I.source_3D_regions * I.fine_axial_intervals * I.egroups;
     float *flux = (float *)malloc((size_t)n_fine * sizeof(float));
     if (!flux) { printf("Error: out of host memory\n"); return EXIT_FAILURE; }
@@ -274,10 +284,12 @@ int main(int argc, char *argv[])
         host_fill(src, n_fine, 0u, I.seed, 0.0f);
         host_fill(flux, n_fine, 1u, I.seed, 0.0f);
         host_fill(sig, n_sig, 2u, I.seed, I.sigt_floor);
-        CHECK(smk_upload(ctx, src, flux, sig));
+        if (multi) CHECK(smk_multi_upload(multi, src, flux, sig));
+        else CHECK(smk_upload(ctx, src, flux, sig));
         free(src); free(sig);
     } else {
-        CHECK(smk_fill_device(ctx, I.sigt_floor));
+        if (multi) CHECK(smk_multi_fill_device(multi, I.sigt_floor));
+        else CHECK(smk_fill_device(ctx, I.sigt_floor));
     }
     printf("Initialization Complete.\n");
     rule();
@@ -285,8 +297,14 @@ int main(int argc, char *argv[])
     centered("SIMULATION");
     rule();
     printf("Attentuating fluxes across segments...\n");
-    double seconds = 0.0;
-    CHECK(smk_run(ctx, 0, smk_num_tracks(I.segments, I.seg_per_thread), &seconds));
+    double seconds = 0.0, kernel_seconds = 0.0;
+    if (multi) {
+        /* runtime = sweep + the one all-reduce of the tallies */
+        CHECK(smk_multi_run(multi, &kernel_seconds, &seconds));
+    } else {
+        CHECK(smk_run(ctx, 0, smk_num_tracks(I.segments, I.seg_per_thread), &seconds));
+        kernel_seconds = seconds;
+    }
     printf("Simulation Complete.\n");
 
     rule();
@@ -297,13 +315,19 @@ int main(int argc, char *argv[])
     printf("%-25s%.3f seconds\n", "Runtime:", seconds);
     printf("%-25s%.8lf ns\n", "Time per Intersection:", tpi);
     printf("%-25s%.4e\n", "Intersections per second:", seconds > 0 ? intersections / seconds : 0.0);
+    if (multi) printf("%-25s%.3f seconds\n", "Slowest GPU kernel:", kernel_seconds);
     rule();
 
     centered("VERIFICATION");
     rule();
     uint64_t checksum = 0;
-    CHECK(smk_download_checksum(ctx, &checksum));
-    CHECK(smk_download_flux(ctx, flux));
+    if (multi) {
+        CHECK(smk_multi_download_checksum(multi, &checksum));
+        CHECK(smk_multi_download_flux(multi, 0, flux));
+    } else {
+        CHECK(smk_download_checksum(ctx, &checksum));
+        CHECK(smk_download_flux(ctx, flux));
+    }
     double sum = 0.0, sumsq = 0.0;
     long nonfinite = 0;
     for (long i = 0; i < n_fine; i++) {
@@ -328,5 +352,6 @@ int main(int argc, char *argv[])
     }
     free(flux);
     smk_destroy(ctx);
+    smk_multi_destroy(multi);
     return 0;
 }

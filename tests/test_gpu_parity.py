@@ -256,3 +256,44 @@ def test_c_driver_printout_and_checksum(smk, oracle, tmp_path):
     assert f"{chk:016x}" in out
     got = np.fromfile(dump, np.float32).reshape(R, F, G)
     assert l2rel(got, want) <= TOL_FAST
+
+
+@pytest.mark.parametrize("allreduce", ["peer", "nccl"])
+def test_multi_gpu_single_process(smk, oracle, allreduce):
+    """smk_multi_*: tracks sharded over every visible GPU, one all-reduce of the tally deltas
+    (NVLink peer-memory kernel or ncclAllReduce); every device ends with the same full flux."""
+    n = smk.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    R, F, G, N, p, seed = 300, 5, 128, 200_000, 100, 61
+    src, flux0, sig = oracle.fill(R, F, G, seed)
+    want = flux0.copy()
+    _, chk_want = oracle.run(src, want, sig, N, p, seed)
+    I = make_input(smk, R, F, G, N, p, seed)
+    with smk.MultiContext(I, n, allreduce) as m:
+        m.upload(src, flux0, sig)
+        ks, ts = m.run()
+        assert 0 < ks <= ts
+        assert m.checksum() == chk_want
+        fluxes = [m.download_flux(d) for d in range(n)]
+    for f in fluxes:
+        assert l2rel(f, want) <= TOL_FAST
+    for f in fluxes[1:]:
+        assert np.array_equal(bits(f), bits(fluxes[0])), "all devices must hold the identical sum"
+
+
+def test_c_driver_multi_gpu(smk, oracle, tmp_path):
+    if smk.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    exe = os.path.join(ROOT, "simplemoc-kernel_b200", "bin", "SimpleMOC-kernel")
+    dump = tmp_path / "flux.bin"
+    r = subprocess.run([exe, "-s", "400000", "-e", "128", "--regions-2d", "200", "--seed", "5", "--gpus", "2",
+                        "--dump-flux", str(dump)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "GPUs:" in r.stdout and "peer-memory" in r.stdout
+    R, F, G, N, p, seed = 270, 5, 128, 400_000, 100, 5
+    src, flux0, sig = oracle.fill(R, F, G, seed)
+    want = flux0.copy()
+    _, chk = oracle.run(src, want, sig, N, p, seed)
+    assert f"{chk:016x}" in r.stdout
+    assert l2rel(np.fromfile(dump, np.float32).reshape(R, F, G), want) <= TOL_FAST
