@@ -723,6 +723,22 @@ int smk_multi_create(const smk_params *p, int n_devices, const int *devices, int
             return fail(SMK_ECUDA, "ncclCommInitAll: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
         }
         m->have_comms = true;
+        // first collective on a communicator sets up its channels (~1 s): do it here, on the
+        // zeroed tallies, so that smk_multi_run times the sweep and not NCCL's lazy initialisation
+        const size_t n = (size_t)(m->ctx[0]->rows * m->ctx[0]->shape.groups_pad);
+        rc = g_nccl.GroupStart();
+        for (int d = 0; d < n_devices && rc == 0; ++d)
+            rc = g_nccl.AllReduce(m->ctx[d]->d_tally, m->ctx[d]->d_tally, n, kNcclFloat32, kNcclSum, m->comms[d],
+                                  m->ctx[d]->stream);
+        if (rc == 0) rc = g_nccl.GroupEnd();
+        for (int d = 0; d < n_devices; ++d) {
+            cudaSetDevice(ids[d]);
+            cudaStreamSynchronize(m->ctx[d]->stream);
+        }
+        if (rc != 0) {
+            smk_multi_destroy(m);
+            return fail(SMK_ECUDA, "NCCL warm-up all-reduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+        }
     }
     *out = m;
     return SMK_OK;
