@@ -5,7 +5,7 @@
 // reference's per-block XORWOW states, /root/reference/src/cuda/kernel.cu:22,52-60)
 // and rand() for the source slabs (/root/reference/src/cpu/init.c:64-75).
 // Pure 32-bit integer arithmetic, identical on host and device; the CPU oracle
-// restates it independently (oracle/smk_oracle.c) and both are pinned to the
+// restates it independently in its own C file and both are pinned to the
 // Random123 Philox4x32-10 known-answer vectors.
 #pragma once
 #include <stdint.h>

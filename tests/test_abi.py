@@ -90,3 +90,19 @@ def test_host_driver_cli_usage():
         assert opt in r.stdout
     r = subprocess.run([exe, "-s"], capture_output=True, text=True)
     assert r.returncode == 1
+
+
+def test_product_does_not_touch_the_oracle():
+    """The oracle is test infrastructure: nothing in the product may import, link, dlopen or run it."""
+    import glob
+    product = glob.glob(os.path.join(ROOT, "simplemoc-kernel_b200", "**", "*.*"), recursive=True) + \
+        glob.glob(os.path.join(ROOT, "include", "*.h")) + [os.path.join(ROOT, "smk_b200.py")]
+    for path in product:
+        if path.endswith((".so", ".o", ".cubin", ".sass", ".log", ".pyc")) or "/build/" in path or "/bin/" in path:
+            continue
+        text = open(path, errors="ignore").read()
+        for needle in ("liboracle", "from oracle", "import oracle", "oracle/", "smk_oracle_", "libref_"):
+            assert needle not in text, f"{path} references {needle!r}"
+    out = subprocess.run(["ldd", os.path.join(ROOT, "simplemoc-kernel_b200", "lib", "libsmk.so")],
+                         capture_output=True, text=True).stdout
+    assert "oracle" not in out and "libref" not in out

@@ -1,0 +1,93 @@
+"""GPU tests at BASELINE.json's FULL config-2 size (128 groups, 1e8 segments, 6750 regions x 5
+intervals, 100 segments per track) through size-independent properties -- the oracle would need
+~1 minute of all host cores for a full replay, so at this size we check:
+  * identical segment -> region indexing: the kernel's fingerprint over all 1e8 segments equals the
+    one computed from the oracle's id stream
+  * sub-sampled replay: in STRICT mode the outgoing psi of sampled track windows is BIT-EXACT
+    against the oracle's replay of exactly those tracks
+  * additivity: sweeping the two halves of the track range on zeroed tallies and adding them
+    reproduces the full sweep (this is what the multi-GPU all-reduce relies on), checksums add
+  * repeatability: two sweeps give the same flux up to the order of the fp32 tally additions
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+R, F, G, N, P, SEED = 6750, 5, 128, 100_000_000, 100, 42
+
+
+def l2rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def full_input(smk, exp_mode="poly", math_mode="fast"):
+    I = smk.Input(segments=N, egroups=G, seg_per_thread=P, seed=SEED, exp_mode=exp_mode, math_mode=math_mode)
+    I.finalize()
+    assert I.source_3D_regions == R
+    return I
+
+
+def oracle_checksum(oracle, seg_begin, seg_end):
+    total = 0
+    step = 5_000_000
+    for s in range(seg_begin, seg_end, step):
+        n = min(step, seg_end - s)
+        q, f = oracle.segment_ids(SEED, s, n, R, F)
+        idx = np.arange(s, s + n, dtype=np.uint64)
+        term = (q.astype(np.uint64) * np.uint64(F) + f.astype(np.uint64) + np.uint64(1)) * ((idx & np.uint64(0xFFFF)) + np.uint64(1))
+        total = (total + int(term.sum(dtype=np.uint64))) % 2 ** 64
+    return total
+
+
+def test_full_size_indexing_fingerprint(smk, oracle):
+    with smk.Context(full_input(smk)) as ctx:
+        ctx.fill_device()
+        ctx.run()
+        got = ctx.checksum()
+    assert got == oracle_checksum(oracle, 0, N)
+
+
+def test_full_size_subsampled_strict_replay(smk, oracle):
+    src, flux0, sig = oracle.fill(R, F, G, SEED)
+    I = full_input(smk, "glibc", "strict")
+    with smk.Context(I, keep_psi=True) as ctx:
+        ctx.fill_device()
+        for tb in (0, 123_456, 500_000, 999_800):          # windows of 200 tracks across the stream
+            te = tb + 200
+            ctx.reset_tallies()
+            ctx.run(tb, te)
+            psi = ctx.download_psi(te - tb)
+            want = np.zeros_like(flux0)
+            psi_want, chk = oracle.run(src, want, sig, N, P, SEED, tb, te, want_psi=True, nthreads=0)
+            assert np.array_equal(psi.view(np.uint32), psi_want.view(np.uint32))
+            assert ctx.checksum() == chk
+            tallies = ctx.download_flux().astype(np.float64) - flux0
+            assert l2rel(tallies, want) <= 5e-6
+
+
+def test_full_size_additivity_and_repeatability(smk):
+    I = full_input(smk)
+    with smk.Context(I) as ctx:
+        ctx.fill_device()
+        ctx.run()
+        full = ctx.download_flux().astype(np.float64)
+        chk_full = ctx.checksum()
+        ctx.reset_tallies()
+        ctx.run()
+        again = ctx.download_flux().astype(np.float64)
+        assert l2rel(again, full) <= 1e-6                    # only the atomic order differs
+        nt = ctx.n_tracks
+        ctx.reset_tallies()
+        ctx.run(0, nt // 2)
+        a, ca = ctx.download_flux().astype(np.float64), ctx.checksum()
+        ctx.reset_tallies()
+        ctx.run(nt // 2, nt)
+        b, cb = ctx.download_flux().astype(np.float64), ctx.checksum()
+        ctx.reset_tallies()
+        ctx.run(0, 0)
+        flux0 = ctx.download_flux().astype(np.float64)       # no segments: initial flux
+    assert (ca + cb) % 2 ** 64 == chk_full
+    assert l2rel(a + b - flux0, full) <= 1e-6
+    assert np.isfinite(full).all()
