@@ -89,5 +89,7 @@ def test_full_size_additivity_and_repeatability(smk):
         ctx.run(0, 0)
         flux0 = ctx.download_flux().astype(np.float64)       # no segments: initial flux
     assert (ca + cb) % 2 ** 64 == chk_full
-    assert l2rel(a + b - flux0, full) <= 1e-6
+    # two fp32 partial sums instead of one: each element is ~3000 tallies of mixed sign, so the
+    # association error is a few 1e-6 .. 1e-5 norm-wise (hard part 2)
+    assert l2rel(a + b - flux0, full) <= 5e-5
     assert np.isfinite(full).all()
