@@ -47,8 +47,9 @@ def parse_args():
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-segments", type=int, default=4_000_000,
-                    help="reference arm: segments per step (bounded sample)")
+    ap.add_argument("--ref-segments", type=int, default=50_000_000,
+                    help="reference arm: segments per step; default = the reference's own README default run "
+                         "(init.c:12: 5e7 segments x 128 groups), BASELINE config 1")
     return ap.parse_args()
 
 
@@ -115,15 +116,16 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the unmodified reference CPU run_kernel on the host cores
 # --------------------------------------------------------------------------------------
-def time_reference(a, steps, warmup, segments):
+def time_reference(a, steps, warmup, segments, variant="ofast"):
     from oracle.oracle import Oracle, Reference
     groups = a.egroups
-    if Reference.available("ofast"):
-        ref = Reference("ofast")
+    if Reference.available(variant):
+        ref = Reference(variant)
         cores = ref.num_procs()
         kind = "reference"
         run = lambda: ref.time_run_kernel(a.regions_2d, groups, segments, cores)  # noqa: E731
-        how = "unmodified /root/reference/src/cpu run_kernel, Makefile gnu flags (-Ofast -msse2 -fopenmp)"
+        how = ("unmodified /root/reference/src/cpu run_kernel, Makefile gnu flags (-Ofast -msse2 -fopenmp)"
+               if variant == "ofast" else f"unmodified /root/reference/src/cpu run_kernel, {variant} build")
     else:  # the reference could not be compiled where this repo was built: time the oracle port
         o = Oracle()
         cores = o.max_threads()
@@ -290,8 +292,15 @@ def main_ours(a):
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu = time_reference(a, steps=3, warmup=1, segments=a.ref_segments)
+        cpu = time_reference(a, steps=2, warmup=1, segments=min(a.ref_segments, 20_000_000))
         cpu.pop("ms_per_step", None)
+        try:   # the same sources built for AVX2+FMA (-march=x86-64-v3): the "fair" CPU figure
+            from oracle.oracle import Reference
+            if Reference.available("v3"):
+                cpu["alt_avx2_fma_build"] = time_reference(a, steps=1, warmup=1, segments=min(a.ref_segments, 20_000_000),
+                                                           variant="v3")["value"]
+        except Exception:
+            pass
 
     if rank == 0:
         line = {

@@ -39,6 +39,8 @@ typedef struct {
     int host_fill;
     float sigt_floor;
     const char *dump_flux;
+    const char *verify_flux;   /* raw float32 flux of a CPU replay of the same stream */
+    double tolerance;
 } Input;
 
 static void rule(void)
@@ -109,6 +111,9 @@ static void usage_and_exit(void)
     puts("  --host-fill           Fill the slabs on the host and upload them");
     puts("  --sigt-floor <x>      Well-conditioned diagnostic data: sigT in [x, 1)");
     puts("  --dump-flux <file>    Write the final scalar flux (raw float32)");
+    puts("  --verify <file>       Compare the flux with a CPU replay of the same stream (raw float32,");
+    puts("                        e.g. from tools/oracle_replay.py) and print PASS/FAIL");
+    puts("  --tolerance <x>       L2-relative tolerance of --verify (default 1e-5)");
     puts("See readme for full description of default run values");
     exit(1);
 }
@@ -142,6 +147,7 @@ static void defaults(Input *I)
     I->exp_mode = SMK_EXP_POLY;
     I->math_mode = SMK_MATH_FAST;
     I->gpus = 1;
+    I->tolerance = 1e-5;
 }
 
 static void parse(int argc, char **argv, Input *I)
@@ -165,6 +171,8 @@ static void parse(int argc, char **argv, Input *I)
         else if (!strcmp(a, "--host-fill")) I->host_fill = 1;
         else if (!strcmp(a, "--sigt-floor")) I->sigt_floor = (float)atof(need(argc, argv, &i));
         else if (!strcmp(a, "--dump-flux")) I->dump_flux = need(argc, argv, &i);
+        else if (!strcmp(a, "--verify")) I->verify_flux = need(argc, argv, &i);
+        else if (!strcmp(a, "--tolerance")) I->tolerance = atof(need(argc, argv, &i));
         else usage_and_exit();
     }
     if (I->nthreads < 1 || I->segments < 0 || I->egroups < 1 || I->seg_per_thread < 1 || I->gpus < 1)
@@ -339,7 +347,35 @@ int main(int argc, char *argv[])
     printf("%-25s%.9e\n", "Scalar Flux Sum:", sum);
     printf("%-25s%.9e\n", "Scalar Flux L2 Norm:", sqrt(sumsq));
     printf("%-25s%ld\n", "Non-finite Flux Values:", nonfinite);
-    printf("%-25s%s\n", "Replay Tolerance:", "1e-5 L2-relative vs CPU oracle (tests/, bench.py)");
+    int verdict = 0;
+    if (I.verify_flux) {
+        /* scalar flux vs a CPU replay of the same stream: same finite pattern and
+         * ||gpu - cpu||_2 / ||cpu||_2 <= tolerance */
+        float *ref = (float *)malloc((size_t)n_fine * sizeof(float));
+        FILE *f = fopen(I.verify_flux, "rb");
+        if (!ref || !f || fread(ref, sizeof(float), (size_t)n_fine, f) != (size_t)n_fine) {
+            printf("Error: cannot read %ld floats from %s\n", n_fine, I.verify_flux);
+            return EXIT_FAILURE;
+        }
+        fclose(f);
+        double num = 0.0, den = 0.0;
+        long pattern = 0;
+        for (long i = 0; i < n_fine; i++) {
+            if (isfinite(flux[i]) != isfinite(ref[i])) { pattern++; continue; }
+            if (!isfinite(ref[i])) continue;
+            const double d = (double)flux[i] - ref[i];
+            num += d * d;
+            den += (double)ref[i] * ref[i];
+        }
+        const double err = den > 0 ? sqrt(num / den) : sqrt(num);
+        verdict = (pattern == 0 && err <= I.tolerance) ? 1 : -1;
+        printf("%-25s%.3e (tolerance %.1e)\n", "L2-relative Error:", err, I.tolerance);
+        printf("%-25s%ld\n", "Finite-pattern Mismatch:", pattern);
+        printf("%-25s%s\n", "Verification:", verdict > 0 ? "PASS" : "FAIL");
+        free(ref);
+    } else {
+        printf("%-25s%s\n", "Verification:", "not requested (--verify <cpu replay flux>)");
+    }
     rule();
 
     if (I.dump_flux) {
@@ -353,5 +389,5 @@ int main(int argc, char *argv[])
     free(flux);
     smk_destroy(ctx);
     smk_multi_destroy(multi);
-    return 0;
+    return verdict < 0 ? 2 : 0;
 }

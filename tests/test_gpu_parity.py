@@ -256,6 +256,16 @@ def test_c_driver_printout_and_checksum(smk, oracle, tmp_path):
     assert f"{chk:016x}" in out
     got = np.fromfile(dump, np.float32).reshape(R, F, G)
     assert l2rel(got, want) <= TOL_FAST
+    # the driver's own verification printout against the CPU replay's flux file
+    ref = tmp_path / "cpu.bin"
+    want.tofile(ref)
+    r = subprocess.run([exe, "-s", "200000", "-e", "64", "-p", "100", "--regions-2d", "100", "--seed", "9",
+                        "--verify", str(ref)], capture_output=True, text=True)
+    assert r.returncode == 0 and "Verification:            PASS" in r.stdout, r.stdout
+    (want * np.float32(1.001)).tofile(ref)
+    r = subprocess.run([exe, "-s", "200000", "-e", "64", "-p", "100", "--regions-2d", "100", "--seed", "9",
+                        "--verify", str(ref)], capture_output=True, text=True)
+    assert r.returncode == 2 and "Verification:            FAIL" in r.stdout
 
 
 @pytest.mark.parametrize("allreduce", ["peer", "nccl"])
