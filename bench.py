@@ -251,6 +251,13 @@ def main_ours(a):
     kernel_ms = kernel_total_ms / a.steps
     peak, peak_kind = measured_peak_gbs()
     achieved = ALGO_BYTES_PER_INTERSECTION * my_segments * G / (kernel_ms * 1e-3) / 1e9
+    # secondary roofline: the FP32 pipe, which is what physically binds on the L2-resident working set
+    # (DESIGN.md section 5.2).  FAST/POLY issues 51 FP32 lane-operations per interior intersection and
+    # 35 per edge intersection (csrc/smk_math.cuh), i.e. (51 (F-2) + 35 * 2) / F on average.
+    lane_ops = (51.0 * (F - 2) + 35.0 * 2) / F
+    sm_hz = (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
+    fp32_peak = torch.cuda.get_device_properties(dev).multi_processor_count * 128 * sm_hz
+    fp32_achieved = lane_ops * my_segments * G / (kernel_ms * 1e-3)
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -318,6 +325,10 @@ def main_ours(a):
                          "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                          "kernel": "attenuate_tracks", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_intersection": ALGO_BYTES_PER_INTERSECTION},
+            "compute_roofline": {"bound": "fp32_pipe", "achieved": fp32_achieved / 1e12, "peak": fp32_peak / 1e12,
+                                 "unit": "T lane-op/s", "frac": fp32_achieved / fp32_peak,
+                                 "lane_ops_per_intersection": lane_ops,
+                                 "note": "valid for --math fast --exp poly; peak = SMs x 128 lanes x SM clock under load"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
             "gpu_launches": launches,
