@@ -108,6 +108,12 @@ CASES = [
     (20,  6, 1000, 5_000,  100, 10),    # NCHUNK = 8
     (50,  5, 128, 1,       100, 11),    # single segment
     (50,  5, 128, 99,      100, 12),    # one short track
+    (1,   5, 128, 5_000,   100, 13),    # a single region: every tally lands on 5 rows
+    (50,  5, 128, 3_000,   1,   14),    # seg_per_track = 1: every segment starts from a fresh psi
+    (50,  5, 64,  777,     1000, 15),   # seg_per_track > segments
+    (50,  5, 128, 10_000,  100, 2**63 + 12345),   # 64-bit seed (both Philox key words in use)
+    (50,  5, 128, 6_400,   64,  17),    # track length = two id batches exactly
+    (50,  5, 128, 6_500,   65,  18),    # track length = two id batches + 1
 ]
 
 
