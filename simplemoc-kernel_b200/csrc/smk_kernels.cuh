@@ -54,8 +54,8 @@ constexpr int kMinBlocksPrefetch = SMK_MIN_BLOCKS_PREFETCH;
 
 __device__ __forceinline__ void red_add_v4(float4 *addr, float a, float b, float c, float d)
 {
-#ifdef SMK_EXPERIMENT_NO_RED   // ceiling experiment only (tools/ubench): keep the math alive, drop the tally
-    asm volatile("" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+#if defined(SMK_EXPERIMENT_NO_RED)   // timing experiment only: plain store instead of the reduction
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 #else
     // one 16-byte vector reduction at L2 per lane (PTX ISA 8.1, sm_90+): SASS RED.E.ADD.F32x4
     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
@@ -487,6 +487,10 @@ template <int NCHUNK, int EXPM>
 __device__ __forceinline__ void compute_by_type(const SegRows<NCHUNK> &r, uint32_t packed, const float2 *s_pairs,
                                                 float4 (&psi)[NCHUNK], float4 (&tally)[NCHUNK])
 {
+#ifdef SMK_EXPERIMENT_ONE_TYPE   // timing experiment only: every segment runs the interior body
+    compute_rows<NCHUNK, EXPM, kFitInterior>(r, s_pairs, psi, tally);
+    return;
+#endif
     if (packed & kFlagFirst)
         compute_rows<NCHUNK, EXPM, kFitFirst>(r, s_pairs, psi, tally);
     else if (packed & kFlagLast)

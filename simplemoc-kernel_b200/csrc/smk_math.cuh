@@ -104,6 +104,9 @@ __device__ __forceinline__ float exp_mufu(float x)
 
 __device__ __forceinline__ float rcp_mufu(float x)
 {
+#ifdef SMK_EXPERIMENT_NO_MUFU   // timing experiment only: wrong values, no XU-pipe instruction
+    return __fmul_rn(x, 0.9f);
+#endif
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
