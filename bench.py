@@ -270,7 +270,7 @@ def main_ours(a):
     flux0 = smk.alloc_pinned((R, F, G))
     sig = smk.alloc_pinned((R, G))
     out = smk.alloc_pinned((R, F, G))
-    rng = np.random.default_rng(a.seed + rank)
+    rng = np.random.default_rng(a.seed)          # every rank holds the same replica of the slabs
     src[...] = rng.random(src.shape, dtype=np.float32)
     flux0[...] = rng.random(flux0.shape, dtype=np.float32)
     sig[...] = rng.random(sig.shape, dtype=np.float32)
