@@ -252,9 +252,9 @@ def main_ours(a):
     peak, peak_kind = measured_peak_gbs()
     achieved = ALGO_BYTES_PER_INTERSECTION * my_segments * G / (kernel_ms * 1e-3) / 1e9
     # secondary roofline: the FP32 pipe, which is what physically binds on the L2-resident working set
-    # (DESIGN.md section 5.2).  FAST/POLY issues 51 FP32 lane-operations per interior intersection and
-    # 35 per edge intersection (csrc/smk_math.cuh), i.e. (51 (F-2) + 35 * 2) / F on average.
-    lane_ops = (51.0 * (F - 2) + 35.0 * 2) / F
+    # (DESIGN.md section 5.2).  FAST/POLY issues 46 FP32 lane-operations per interior intersection and
+    # 30 per edge intersection (csrc/smk_math.cuh), i.e. (46 (F-2) + 30 * 2) / F on average.
+    lane_ops = (46.0 * (F - 2) + 30.0 * 2) / F
     sm_hz = (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
     fp32_peak = torch.cuda.get_device_properties(dev).multi_processor_count * 128 * sm_hz
     fp32_achieved = lane_ops * my_segments * G / (kernel_ms * 1e-3)

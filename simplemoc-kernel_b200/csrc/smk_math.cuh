@@ -182,45 +182,6 @@ __device__ __forceinline__ FitCoeffs fit_coeffs(bool first, bool last)
     return f;
 }
 
-// FAST: one intersection.  y1 / y3 must be finite (0) when the row is not loaded.
-template <int EXPM>
-__device__ __forceinline__ void attenuate_fast(const FitCoeffs &f, float y1, float y2, float y3,
-                                               float sigT, const float2 *s_pairs, float &psi,
-                                               float &tally)
-{
-    const float q0 = fmaf(f.c0, y3, fmaf(f.b0, y2, f.a0 * y1));
-    const float Q1 = fmaf(f.c1, y3, fmaf(f.b1, y2, f.a1 * y1));   // mu  * q1
-    const float Q2 = fmaf(f.c2, y3, fmaf(f.b2, y2, f.a2 * y1));   // mu2 * q2
-
-    const float tau = sigT * Geometry::ds;
-    float e;
-    const float ev = exp_val<EXPM>(tau, s_pairs, e);
-
-    const float rs = rcp_mufu(sigT);
-    const float rs2 = rs * rs;
-    // reuse = tau (tau - 2) + 2 expVal / sigT^3           (kernel.c:235-236)
-    const float reuse = fmaf(2.0f, ev * (rs2 * rs), tau * (tau - 2.0f));
-    // (q0 tau + (sigT psi - q0) expVal) / sigT^2          (kernel.c:248-249)
-    const float n1 = fmaf(fmaf(sigT, psi, -q0), ev, q0 * tau);
-    // tau (tau (tau - 3) + 6) - 6 expVal                  (kernel.c:250)
-    // NOT contracted: the true value is ~tau^4/4 while the terms are ~6 tau, so for small
-    // sigT the result is pure rounding noise (cancellation factor 24/tau^3) that is then
-    // divided by 3 sigT^4 and reaches 1e-4 of the dominant term.  Parity with the reference
-    // needs the reference's own roundings here; measured (gpurun r01a, reproduced by CPU
-    // emulation): contracted 1.2e-4 L2-relative, reference order 3.6e-8.
-    const float p3 = __fsub_rn(__fmul_rn(tau, __fadd_rn(__fmul_rn(tau, __fsub_rn(tau, 3.0f)), 6.0f)),
-                               __fmul_rn(6.0f, ev));
-    const float w3 = (Q2 * (1.0f / 3.0f)) * (p3 * (rs2 * rs2));   // kernel.c:250-251
-    const float flux_integral = fmaf(n1, rs2, fmaf(Q1, reuse, w3));
-    tally = Geometry::weight * flux_integral;                      // kernel.c:262
-
-    // psi_out = t1 + t2 + t3 + t4                         (kernel.c:291-331)
-    float acc = (q0 * ev) * rs;
-    acc = fmaf(Q1 * (tau - ev), rs2, acc);
-    acc = fmaf(Q2, reuse, acc);
-    psi = fmaf(psi, e, acc);
-}
-
 // ------------------------------------------------------------------------------
 // FAST, packed: two intersections (two adjacent energy groups) per instruction with the
 // sm_100 FP32x2 datapath (PTX fma/mul/add.rn.f32x2, SASS FFMA2 / FMUL2 / FADD2).  Every
@@ -266,18 +227,20 @@ struct FitDiff {
 
 // e = exp(-tau) on both halves; returns expVal = 1 - e
 template <int EXPM>
-__device__ __forceinline__ float2 exp_val2(float2 tau, float2 sigT, const float2 *s_pairs, float2 &e_out)
+__device__ __forceinline__ float2 exp_val2(float2 tau, const float2 *s_pairs, float2 &e_out, float2 &tau2_out)
 {
     if constexpr (EXPM == kExpPoly) {
-        const float2 x = mul2(sigT, f2(-Geometry::ds));             // -tau, exactly
-        float2 p = fma2(f2(0x1.415ffep-13f), x, f2(0x1.6336e4p-10f));
-        p = fma2(p, x, f2(0x1.10ac84p-7f));
-        p = fma2(p, x, f2(0x1.555146p-5f));
-        p = fma2(p, x, f2(0x1.555546p-3f));
-        p = fma2(p, x, f2(0.5f));
-        const float2 x2 = mul2(x, x);
-        const float2 s = add2(x, f2(1.0f));
-        const float2 lost = sub2(x, add2(s, f2(-1.0f)));            // exact: (1 + x) - s
+        // exp_poly() on both halves, written in tau = -x: the odd coefficients change sign, every
+        // intermediate is the same number up to sign, so e is bit-identical to exp_poly(-tau)
+        float2 p = fma2(f2(-0x1.415ffep-13f), tau, f2(0x1.6336e4p-10f));
+        p = fma2(p, tau, f2(-0x1.10ac84p-7f));
+        p = fma2(p, tau, f2(0x1.555146p-5f));
+        p = fma2(p, tau, f2(-0x1.555546p-3f));
+        p = fma2(p, tau, f2(0.5f));
+        const float2 x2 = mul2(tau, tau);
+        tau2_out = x2;
+        const float2 s = fma2(tau, f2(-1.0f), f2(1.0f));             // RN(1 - tau)
+        const float2 lost = fma2(tau, f2(-1.0f), sub2(f2(1.0f), s)); // exact: (1 - tau) - s
         const float2 e = add2(s, fma2(x2, p, lost));
         e_out = e;
         return sub2(f2(1.0f), e);
@@ -285,6 +248,7 @@ __device__ __forceinline__ float2 exp_val2(float2 tau, float2 sigT, const float2
         float ex, ey;
         const float evx = exp_val<EXPM>(tau.x, s_pairs, ex);
         const float evy = exp_val<EXPM>(tau.y, s_pairs, ey);
+        tau2_out = mul2(tau, tau);
         e_out = make_float2(ex, ey);
         return make_float2(evx, evy);
     }
@@ -323,34 +287,34 @@ __device__ __forceinline__ void attenuate_fast2(const FitCoeffs &f, float2 y1, f
     }
 
     const float2 tau = mul2(sigT, f2(Geometry::ds));
-    float2 e;
-    const float2 ev = exp_val2<EXPM>(tau, sigT, s_pairs, e);
+    float2 e, tau2;
+    const float2 ev = exp_val2<EXPM>(tau, s_pairs, e, tau2);
     const float2 tme = sub2(tau, ev);                               // tau - expVal (exact)
 
     const float2 rs = make_float2(rcp_mufu(sigT.x), rcp_mufu(sigT.y));
     const float2 rs2 = mul2(rs, rs);
-    // reuse = tau (tau - 2) + 2 expVal / sigT^3             (kernel.c:235-236)
-    const float2 reuse = fma2(f2(2.0f), mul2(ev, mul2(rs2, rs)), mul2(tau, add2(tau, f2(-2.0f))));
-    // q0 tau + (sigT psi - q0) expVal = q0 (tau - expVal) + sigT psi expVal   (kernel.c:248)
-    const float2 n1 = fma2(q0, tme, mul2(mul2(sigT, psi), ev));
-    float2 fi;
+    // E = expVal / sigT and Fc = (tau - expVal) / sigT^2 serve both the flux integral
+    //   (q0 tau + (sigT psi - q0) expVal) / sigT^2 = q0 Fc + psi E                  (kernel.c:248-249)
+    // and the outgoing flux  t1 + t2 = q0 E + mu q1 Fc                              (kernel.c:291,301)
+    const float2 E = mul2(ev, rs);
+    const float2 Fc = mul2(tme, rs2);
+    // reuse = tau (tau - 2) + 2 expVal / sigT^3 = (tau^2 - 2 tau) + 2 E / sigT^2   (kernel.c:235-236)
+    const float2 reuse = fma2(f2(2.0f), mul2(E, rs2), fma2(tau, f2(-2.0f), tau2));
+    float2 fi = fma2(Q1, reuse, fma2(q0, Fc, mul2(psi, E)));
+    float2 acc = mul2(psi, e);                                       // t4 = psi (1 - expVal), kernel.c:321
     if constexpr (kQuadratic) {
-        // tau (tau (tau - 3) + 6) - 6 expVal in the reference's order (see attenuate_fast)
+        // tau (tau (tau - 3) + 6) - 6 expVal, kernel.c:250, evaluated in the reference's order and NOT
+        // contracted: its true value is ~tau^4/4 while its terms are ~6 tau, so for small sigT it is
+        // pure rounding noise (cancellation factor 24/tau^3) that, divided by 3 sigT^4, reaches 1e-4
+        // of the dominant term.  Parity needs the reference's own roundings here; measured (gpurun
+        // r01a, reproduced by CPU emulation): contracted 1.2e-4 L2-relative, reference order 3.6e-8.
         const float2 cubic = sub2(mul2(tau, add2(mul2(tau, add2(tau, f2(-3.0f))), f2(6.0f))),
                                   mul2(f2(6.0f), ev));
-        const float2 w3 = mul2(mul2(Q2, f2(1.0f / 3.0f)), mul2(cubic, mul2(rs2, rs2)));
-        fi = fma2(Q1, reuse, w3);
-    } else {
-        fi = mul2(Q1, reuse);
+        fi = fma2(mul2(Q2, f2(1.0f / 3.0f)), mul2(cubic, mul2(rs2, rs2)), fi);         // kernel.c:250-251
+        acc = fma2(Q2, reuse, acc);                                                     // t3, kernel.c:311
     }
-    fi = fma2(n1, rs2, fi);
-    tally = mul2(f2(Geometry::weight), fi);                         // kernel.c:262
-
-    // psi_out = t1 + t2 + t3 + t4                           (kernel.c:291-331)
-    float2 acc = mul2(mul2(q0, ev), rs);
-    acc = fma2(mul2(Q1, tme), rs2, acc);
-    if constexpr (kQuadratic) acc = fma2(Q2, reuse, acc);
-    psi = fma2(psi, e, acc);
+    tally = mul2(f2(Geometry::weight), fi);                          // kernel.c:262
+    psi = fma2(q0, E, fma2(Q1, Fc, acc));                            // kernel.c:331
 }
 
 // STRICT: one intersection in the reference's own operation order.
