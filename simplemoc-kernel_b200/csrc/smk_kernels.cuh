@@ -610,14 +610,50 @@ attenuate_tracks_pf(const KernelArgs a)
             }
             if (nseg > 0) red_row<NCHUNK>(a.tally, pend, lane, t);
         } else {
-            for (int s = 0; s < nseg; ++s) {
-                SegRows<NCHUNK> r;
-                const uint32_t pk = __shfl_sync(kFull, cur_packed, s & 31);
-                const uint32_t qs = __shfl_sync(kFull, cur_qsr, s & 31);
-                load_rows<NCHUNK>(r, a.source, a.sigT, pk, qs, lane);
-                compute_by_type<NCHUNK, EXPM>(r, pk, s_pairs, psi, t);
-                red_row<NCHUNK>(a.tally, pk, lane, t);
-                rotate(s);
+            // batches of 32 segments (one id per lane); inside a batch: branch on the warp-uniform
+            // segment type first, then load only the rows that type reads, compute, RED
+            for (int b = 0; b < nseg; b += 32) {
+                const int count = (nseg - b) < 32 ? (nseg - b) : 32;
+                for (int k = 0; k < count; ++k) {
+                    const uint32_t pk = __shfl_sync(kFull, cur_packed, k);
+                    const uint32_t qs = __shfl_sync(kFull, cur_qsr, k);
+                    const uint32_t off = (pk & kRowMask) * (uint32_t)ROWF4 + (uint32_t)lane;
+                    const float4 *src = a.source + off;
+                    const float4 *sig = a.sigT + (qs * (uint32_t)ROWF4 + (uint32_t)lane);
+                    SegRows<NCHUNK> r;
+                    if (pk & kFlagFirst) {
+#pragma unroll
+                        for (int c = 0; c < NCHUNK; ++c) {
+                            r.y2[c] = ldg4(src + c * 32);
+                            r.y3[c] = ldg4(src + c * 32 + ROWF4);
+                            r.st[c] = ldg4(sig + c * 32);
+                        }
+                        compute_rows<NCHUNK, EXPM, kFitFirst>(r, s_pairs, psi, t);
+                    } else if (pk & kFlagLast) {
+#pragma unroll
+                        for (int c = 0; c < NCHUNK; ++c) {
+                            r.y1[c] = ldg4(src + c * 32 - ROWF4);
+                            r.y2[c] = ldg4(src + c * 32);
+                            r.st[c] = ldg4(sig + c * 32);
+                        }
+                        compute_rows<NCHUNK, EXPM, kFitLast>(r, s_pairs, psi, t);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < NCHUNK; ++c) {
+                            r.y1[c] = ldg4(src + c * 32 - ROWF4);
+                            r.y2[c] = ldg4(src + c * 32);
+                            r.y3[c] = ldg4(src + c * 32 + ROWF4);
+                            r.st[c] = ldg4(sig + c * 32);
+                        }
+                        compute_rows<NCHUNK, EXPM, kFitInterior>(r, s_pairs, psi, t);
+                    }
+                    float4 *tal = reinterpret_cast<float4 *>(a.tally) + off;
+#pragma unroll
+                    for (int c = 0; c < NCHUNK; ++c) red_add_v4(tal + c * 32, t[c].x, t[c].y, t[c].z, t[c].w);
+                }
+                cur_packed = nxt_packed;
+                cur_qsr = nxt_qsr;
+                draw(s0, b + 64 + lane, nseg, nxt_packed, nxt_qsr);
             }
         }
 
