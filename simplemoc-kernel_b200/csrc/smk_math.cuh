@@ -142,43 +142,37 @@ __device__ __forceinline__ float exp_val(float tau, const float2 *s_pairs, float
 }
 
 // --------------------------------------------------------------------------
-// Quadratic / linear axial source fit (kernel.c:111-191) as coefficients of
-// (y1, y2, y3) = fine_source[QSR][FAI-1 .. FAI+1][g], constants folded:
-//   interior : q0 = 6 y1 - 8 y2 + 3 y3, q1 = 35 y1 - 60 y2 + 25 y3, q2 = 50 (y1 - 2 y2 + y3)
-//   FAI == 0 : q0 = -2 y2 + 3 y3,       q1 = 10 (y3 - y2),          q2 = 0
-//   FAI == F-1: q0 = -3 y1 + 4 y2,      q1 = 10 (y2 - y1),          q2 = 0
-// (dz = 0.1, zin = 0.3).  q1 and q2 are returned pre-multiplied by mu and mu2.
+// Quadratic / linear axial source fit (kernel.c:111-191) in difference form, constants folded
+// (dz = 0.1, zin = 0.3; q1, q2 pre-multiplied by mu, mu2):
+//   d = y1 - y3,  s = y1 - 2 y2 + y3   with (y1, y2, y3) = fine_source[QSR][FAI-1 .. FAI+1][g]
+//   q0 = y2 + q0_d d + q0_s s,   mu q1 = q1_d d + q1_s s,   mu2 q2 = q2_s s
+//   interior   : ( 1.5,  4.5,  4.5, 27  , 15)   c1 = d / (2 dz), c2 = s / (2 dz^2)   (kernel.c:182-189)
+//   FAI == 0   : (-1.5,  1.5, -4.5,  4.5,  0)   with y1 := 0:  c1 = (y3 - y2) / dz   (kernel.c:128-134)
+//   FAI == F-1 : (-1.5, -1.5, -4.5, -4.5,  0)   with y3 := 0:  c1 = (y2 - y1) / dz   (kernel.c:154-160)
+// Per-lane coefficients are only needed where lanes of one warp serve tracks of different types.
 // --------------------------------------------------------------------------
+struct FitDiff {
+    static constexpr float dz = Geometry::dz, zin = Geometry::zin, mu = Geometry::mu, mu2 = Geometry::mu2;
+    static constexpr float k1 = 1.0f / (2.0f * dz), k2 = 1.0f / (2.0f * dz * dz);
+    static constexpr float q0_d = k1 * zin, q0_s = k2 * zin * zin;          // 1.5, 4.5
+    static constexpr float q1_d = mu * k1, q1_s = mu * 2.0f * k2 * zin;     // 4.5, 27
+    static constexpr float q2_s = mu2 * k2;                                 // 15
+    static constexpr float e0 = zin / dz, e1 = mu / dz;                     // 3, 9
+};
+
 struct FitCoeffs {
-    float a0, b0, c0;   // q0
-    float a1, b1, c1;   // mu  * q1
-    float a2, b2, c2;   // mu2 * q2
+    float q0_d, q0_s, q1_d, q1_s, q2_s;
 };
 
 __device__ __forceinline__ FitCoeffs fit_coeffs(bool first, bool last)
 {
-    constexpr float dz = Geometry::dz, zin = Geometry::zin;
-    constexpr float mu = Geometry::mu, mu2 = Geometry::mu2;
-    // interior: c1 = (y1 - y3) / (2 dz), c2 = (y1 - 2 y2 + y3) / (2 dz^2)
-    constexpr float k1 = 1.0f / (2.0f * dz), k2 = 1.0f / (2.0f * dz * dz);
-    constexpr float ia0 = k1 * zin + k2 * zin * zin, ib0 = 1.0f - 2.0f * k2 * zin * zin,
-                    ic0 = -k1 * zin + k2 * zin * zin;
-    constexpr float ia1 = mu * (k1 + 2.0f * k2 * zin), ib1 = mu * (-4.0f * k2 * zin),
-                    ic1 = mu * (-k1 + 2.0f * k2 * zin);
-    constexpr float ia2 = mu2 * k2, ib2 = mu2 * -2.0f * k2, ic2 = mu2 * k2;
-    // edges: c1 = (y3 - y2) / dz resp. (y2 - y1) / dz
-    constexpr float e = 1.0f / dz;
-    FitCoeffs f;
-    f.a0 = first ? 0.0f : (last ? -e * zin : ia0);
-    f.b0 = first ? 1.0f - e * zin : (last ? 1.0f + e * zin : ib0);
-    f.c0 = first ? e * zin : (last ? 0.0f : ic0);
-    f.a1 = first ? 0.0f : (last ? -mu * e : ia1);
-    f.b1 = first ? -mu * e : (last ? mu * e : ib1);
-    f.c1 = first ? mu * e : (last ? 0.0f : ic1);
     const bool edge = first || last;
-    f.a2 = edge ? 0.0f : ia2;
-    f.b2 = edge ? 0.0f : ib2;
-    f.c2 = edge ? 0.0f : ic2;
+    FitCoeffs f;
+    f.q0_d = edge ? -0.5f * FitDiff::e0 : FitDiff::q0_d;
+    f.q0_s = first ? 0.5f * FitDiff::e0 : (last ? -0.5f * FitDiff::e0 : FitDiff::q0_s);
+    f.q1_d = edge ? -0.5f * FitDiff::e1 : FitDiff::q1_d;
+    f.q1_s = first ? 0.5f * FitDiff::e1 : (last ? -0.5f * FitDiff::e1 : FitDiff::q1_s);
+    f.q2_s = edge ? 0.0f : FitDiff::q2_s;
     return f;
 }
 
@@ -197,33 +191,6 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, f2(-1.0f), a); }
 
 enum : int { kFitInterior = 0, kFitFirst = 1, kFitLast = 2, kFitDynamic = 3 };
-
-// the nine coefficients of fit_coeffs() as compile-time constants per segment type
-template <int FIT>
-struct FitConst {
-    static constexpr float dz = Geometry::dz, zin = Geometry::zin, mu = Geometry::mu, mu2 = Geometry::mu2;
-    static constexpr float k1 = 1.0f / (2.0f * dz), k2 = 1.0f / (2.0f * dz * dz), e = 1.0f / dz;
-    static constexpr bool first = FIT == kFitFirst, last = FIT == kFitLast;
-    static constexpr float a0 = first ? 0.0f : (last ? -e * zin : k1 * zin + k2 * zin * zin);
-    static constexpr float b0 = first ? 1.0f - e * zin : (last ? 1.0f + e * zin : 1.0f - 2.0f * k2 * zin * zin);
-    static constexpr float c0 = first ? e * zin : (last ? 0.0f : -k1 * zin + k2 * zin * zin);
-    static constexpr float a1 = first ? 0.0f : (last ? -mu * e : mu * (k1 + 2.0f * k2 * zin));
-    static constexpr float b1 = first ? -mu * e : (last ? mu * e : mu * (-4.0f * k2 * zin));
-    static constexpr float c1 = first ? mu * e : (last ? 0.0f : mu * (-k1 + 2.0f * k2 * zin));
-    static constexpr float a2 = (first || last) ? 0.0f : mu2 * k2;
-    static constexpr float b2 = (first || last) ? 0.0f : mu2 * -2.0f * k2;
-    static constexpr float c2 = (first || last) ? 0.0f : mu2 * k2;
-};
-
-// fit coefficients in difference form (one operation fewer than the y1/y2/y3 form)
-struct FitDiff {
-    static constexpr float dz = Geometry::dz, zin = Geometry::zin, mu = Geometry::mu, mu2 = Geometry::mu2;
-    static constexpr float k1 = 1.0f / (2.0f * dz), k2 = 1.0f / (2.0f * dz * dz);
-    static constexpr float q0_d = k1 * zin, q0_s = k2 * zin * zin;          // 1.5, 4.5
-    static constexpr float q1_d = mu * k1, q1_s = mu * 2.0f * k2 * zin;     // 4.5, 27
-    static constexpr float q2_s = mu2 * k2;                                 // 15
-    static constexpr float e0 = zin / dz, e1 = mu / dz;                     // 3, 9
-};
 
 // e = exp(-tau) on both halves; returns expVal = 1 - e
 template <int EXPM>
@@ -265,9 +232,11 @@ __device__ __forceinline__ void attenuate_fast2(const FitCoeffs &f, float2 y1, f
     constexpr bool kQuadratic = (FIT == kFitInterior) || (FIT == kFitDynamic);
     float2 q0, Q1, Q2 = f2(0.0f);
     if constexpr (FIT == kFitDynamic) {
-        q0 = fma2(f2(f.c0), y3, fma2(f2(f.b0), y2, mul2(f2(f.a0), y1)));
-        Q1 = fma2(f2(f.c1), y3, fma2(f2(f.b1), y2, mul2(f2(f.a1), y1)));
-        Q2 = fma2(f2(f.c2), y3, fma2(f2(f.b2), y2, mul2(f2(f.a2), y1)));
+        const float2 d = sub2(y1, y3);
+        const float2 s = fma2(y2, f2(-2.0f), add2(y1, y3));
+        q0 = fma2(f2(f.q0_s), s, fma2(f2(f.q0_d), d, y2));
+        Q1 = fma2(f2(f.q1_s), s, mul2(f2(f.q1_d), d));
+        Q2 = mul2(f2(f.q2_s), s);
     } else if constexpr (FIT == kFitInterior) {
         // d = y1 - y3, s = y1 - 2 y2 + y3:  c1 = d / (2 dz), c2 = s / (2 dz^2)   (kernel.c:182-184)
         using K = FitDiff;
