@@ -148,23 +148,24 @@ static AttenuateFn pick_staged_exp(int expm)
     return nullptr;
 }
 
-template <int NCHUNK, bool PREFETCH, bool DEFER = false>
+template <int NCHUNK, bool PREFETCH, bool DEFER = false, bool L1PF = false>
 static AttenuateFn pick_pf_exp(int expm)
 {
     switch (expm) {
-        case kExpPoly: return attenuate_tracks_pf<NCHUNK, kExpPoly, PREFETCH, DEFER>;
-        case kExpMufu: return attenuate_tracks_pf<NCHUNK, kExpMufu, PREFETCH, DEFER>;
-        case kExpGlibc: return attenuate_tracks_pf<NCHUNK, kExpGlibc, PREFETCH, DEFER>;
-        case kExpTable: return attenuate_tracks_pf<NCHUNK, kExpTable, PREFETCH, DEFER>;
+        case kExpPoly: return attenuate_tracks_pf<NCHUNK, kExpPoly, PREFETCH, DEFER, L1PF>;
+        case kExpMufu: return attenuate_tracks_pf<NCHUNK, kExpMufu, PREFETCH, DEFER, L1PF>;
+        case kExpGlibc: return attenuate_tracks_pf<NCHUNK, kExpGlibc, PREFETCH, DEFER, L1PF>;
+        case kExpTable: return attenuate_tracks_pf<NCHUNK, kExpTable, PREFETCH, DEFER, L1PF>;
     }
     return nullptr;
 }
 
 // flat-loop kernels for the one-track-per-warp shapes, FAST math: "flat" (loads at use) and
 // "prefetch" (software-pipelined through a second register set)
-static AttenuateFn pick_flat(const Shape &s, int math, int expm, bool prefetch, bool defer = false)
+static AttenuateFn pick_flat(const Shape &s, int math, int expm, bool prefetch, bool defer = false, bool l1pf = false)
 {
     if (math != kMathFast || s.lpt != 32) return nullptr;
+    if (l1pf) return s.nchunk == 1 ? pick_pf_exp<1, false, false, true>(expm) : nullptr;
     if (defer) return s.nchunk == 1 ? pick_pf_exp<1, false, true>(expm) : nullptr;
     if (prefetch) return s.nchunk == 1 ? pick_pf_exp<1, true>(expm) : nullptr;
     switch (s.nchunk) {
@@ -287,13 +288,14 @@ int smk_create(const smk_params *p, smk_ctx **out)
     c->shape = shape;
     c->kernel = pick_kernel(shape, p->math_mode, p->exp_mode);
     // Kernel variants.  Default: the flat-loop kernel where it exists (one track per warp, FAST
-    // math), else the general kernel.  SMK_KERNEL = direct | flat | defer | prefetch | staged2 |
+    // math), else the general kernel.  SMK_KERNEL = direct | flat | l1pf | defer | prefetch | staged2 |
     // staged3 selects another variant for the tuning experiments recorded in DESIGN.md section 5.3.
     const char *variant = getenv("SMK_KERNEL");
     if (!variant || !*variant) variant = "flat";
-    if (strcmp(variant, "flat") == 0 || strcmp(variant, "prefetch") == 0 || strcmp(variant, "defer") == 0) {
+    if (strcmp(variant, "flat") == 0 || strcmp(variant, "prefetch") == 0 || strcmp(variant, "defer") == 0 ||
+        strcmp(variant, "l1pf") == 0) {
         AttenuateFn pf = pick_flat(shape, p->math_mode, p->exp_mode, strcmp(variant, "prefetch") == 0,
-                                   strcmp(variant, "defer") == 0);
+                                   strcmp(variant, "defer") == 0, strcmp(variant, "l1pf") == 0);
         if (pf) c->kernel = pf;
     } else if (strncmp(variant, "staged", 6) == 0) {
         const int stages = atoi(variant + 6);

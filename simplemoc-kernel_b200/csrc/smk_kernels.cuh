@@ -65,6 +65,11 @@ __device__ __forceinline__ void red_add_v4(float4 *addr, float a, float b, float
 #endif
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ float4 ldg4(const float4 *p)
 {
 #ifdef SMK_EXPERIMENT_NO_LDG   // ceiling experiment only: synthesise the row from the address, no memory access
@@ -508,7 +513,7 @@ __device__ __forceinline__ void red_row(float *tally_base, uint32_t packed, int 
     for (int c = 0; c < NCHUNK; ++c) red_add_v4(tal + c * 32, t[c].x, t[c].y, t[c].z, t[c].w);
 }
 
-template <int NCHUNK, int EXPM, bool PREFETCH, bool DEFER>
+template <int NCHUNK, int EXPM, bool PREFETCH, bool DEFER, bool L1PF = false>
 __global__ void __launch_bounds__(kThreadsPerBlock, (NCHUNK == 1) ? (PREFETCH ? kMinBlocksPrefetch : kMinBlocksFast) : 1)
 attenuate_tracks_pf(const KernelArgs a)
 {
@@ -620,6 +625,21 @@ attenuate_tracks_pf(const KernelArgs a)
                     const uint32_t off = (pk & kRowMask) * (uint32_t)ROWF4 + (uint32_t)lane;
                     const float4 *src = a.source + off;
                     const float4 *sig = a.sigT + (qs * (uint32_t)ROWF4 + (uint32_t)lane);
+                    if constexpr (L1PF) {
+                        // pull the rows of the NEXT segment of this batch into L1 while this one is computed
+                        // (no registers held; the loads of the next iteration then hit L1)
+                        const int kn = (k + 1 < count) ? k + 1 : k;
+                        const uint32_t pkn = __shfl_sync(kFull, cur_packed, kn);
+                        const uint32_t qsn = __shfl_sync(kFull, cur_qsr, kn);
+                        const float4 *srcn = a.source + ((pkn & kRowMask) * (uint32_t)ROWF4 + (uint32_t)lane);
+#pragma unroll
+                        for (int c = 0; c < NCHUNK; ++c) {
+                            prefetch_l1(srcn + c * 32);
+                            if (!(pkn & kFlagFirst)) prefetch_l1(srcn + c * 32 - ROWF4);
+                            if (!(pkn & kFlagLast)) prefetch_l1(srcn + c * 32 + ROWF4);
+                            prefetch_l1(a.sigT + (qsn * (uint32_t)ROWF4 + (uint32_t)lane) + c * 32);
+                        }
+                    }
                     SegRows<NCHUNK> r;
                     if (pk & kFlagFirst) {
 #pragma unroll
