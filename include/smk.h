@@ -139,11 +139,12 @@ int   smk_run_host(const smk_params *p, const float *fine_source,
 
 /* ---- plumbing for callers that own device memory (torch, NCCL) --------- */
 /* raw device pointers of the context's padded arrays (void* = float*) */
-void *smk_device_tally(smk_ctx *ctx);      /* [R][F][G_pad], the all-reduce operand */
+void *smk_device_tally(smk_ctx *ctx);      /* [replicas][R][F][G_pad], the all-reduce operand;
+                                              replicas > 1 only when R*F < 4096 (contention relief) */
 void *smk_device_flux0(smk_ctx *ctx);      /* [R][F][G_pad] initial flux            */
 void *smk_device_source(smk_ctx *ctx);     /* [R][F][G_pad]                         */
 void *smk_device_sigT(smk_ctx *ctx);       /* [R][G_pad]                            */
-int64_t smk_padded_elems(const smk_ctx *ctx); /* R*F*G_pad                          */
+int64_t smk_padded_elems(const smk_ctx *ctx); /* replicas*R*F*G_pad: floats behind smk_device_tally */
 /* pinned host memory for end-to-end runs */
 void *smk_alloc_host(size_t bytes);
 void  smk_free_host(void *p);

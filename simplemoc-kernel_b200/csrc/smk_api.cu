@@ -197,6 +197,7 @@ struct smk_ctx {
     int sm_count;
     int blocks_per_sm;
     int64_t rows;            // R * F
+    int replicas;            // copies of the tally array (contention relief for few-row problems)
     int64_t n_tracks;
     float *d_source, *d_sigT, *d_flux0, *d_tally;
     float *d_stage;          // unpadded staging, R*F*G floats
@@ -315,6 +316,17 @@ int smk_create(const smk_params *p, smk_ctx **out)
                     p->exp_mode);
     }
     c->rows = (int64_t)p->source_3D_regions * p->fine_axial_intervals;
+    // few tally rows => L2 atomics on the same addresses serialise: spread them over replicas so that
+    // at least ~4096 rows are in play (1 for the reference's default 33750 rows)
+    c->replicas = 1;
+    if (c->rows < 4096) {
+        c->replicas = (int)((4096 + c->rows - 1) / c->rows);
+        if (c->replicas > 32) c->replicas = 32;
+    }
+    if (const char *r = getenv("SMK_TALLY_REPLICAS")) {       // tuning knob, like SMK_KERNEL
+        const int v = atoi(r);
+        if (v >= 1 && v <= 256) c->replicas = v;
+    }
     c->n_tracks = smk_num_tracks(p->segments, p->seg_per_track);
 
     cudaDeviceProp prop;
@@ -337,14 +349,14 @@ int smk_create(const smk_params *p, smk_ctx **out)
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(&c->d_source, slab);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_flux0, slab);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_tally, slab);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_tally, slab * c->replicas);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_sigT, sig);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_stage, stage);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_checksum, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) { c->own_stream = true; e = cudaEventCreate(&c->ev0); }
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
-    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tally, 0, slab, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tally, 0, slab * c->replicas, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_flux0, 0, slab, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_checksum, 0, sizeof(unsigned long long), c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -411,7 +423,8 @@ int smk_reset_tallies(smk_ctx *c)
 {
     if (!c) return fail(SMK_EINVAL, "ctx is NULL");
     SMK_CUDA(cudaSetDevice(c->p.device));
-    SMK_CUDA(cudaMemsetAsync(c->d_tally, 0, (size_t)c->rows * c->shape.groups_pad * sizeof(float), c->stream));
+    SMK_CUDA(cudaMemsetAsync(c->d_tally, 0, (size_t)c->rows * c->shape.groups_pad * sizeof(float) * c->replicas,
+                             c->stream));
     SMK_CUDA(cudaMemsetAsync(c->d_checksum, 0, sizeof(unsigned long long), c->stream));
     return SMK_OK;
 }
@@ -482,6 +495,8 @@ static int launch(smk_ctx *c, int64_t track_begin, int64_t track_end)
     a.source = reinterpret_cast<const float4 *>(c->d_source);
     a.sigT = reinterpret_cast<const float4 *>(c->d_sigT);
     a.tally = c->d_tally;
+    a.replica_stride = c->rows * c->shape.groups_pad;
+    a.replicas = c->replicas;
     a.psi_out = (c->p.flags & SMK_FLAG_KEEP_PSI) ? c->d_psi : nullptr;
     a.checksum = c->d_checksum;
     a.segments = c->p.segments;
@@ -540,7 +555,8 @@ int smk_download_flux(smk_ctx *c, float *out)
     if (!c || !out) return fail(SMK_EINVAL, "NULL argument");
     SMK_CUDA(cudaSetDevice(c->p.device));
     const int G = c->p.egroups, Gp = c->shape.groups_pad;
-    finalize_flux<<<layout_grid(c->rows * G), 256, 0, c->stream>>>(c->d_flux0, c->d_tally, c->d_stage, c->rows, G, Gp);
+    finalize_flux<<<layout_grid(c->rows * G), 256, 0, c->stream>>>(c->d_flux0, c->d_tally, c->d_stage, c->rows, G, Gp,
+                                                                 c->replicas);
     SMK_CUDA(cudaGetLastError());
     c->launches += 1;
     SMK_CUDA(cudaMemcpyAsync(out, c->d_stage, (size_t)c->rows * G * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -727,7 +743,7 @@ int smk_multi_create(const smk_params *p, int n_devices, const int *devices, int
         m->have_comms = true;
         // first collective on a communicator sets up its channels (~1 s): do it here, on the
         // zeroed tallies, so that smk_multi_run times the sweep and not NCCL's lazy initialisation
-        const size_t n = (size_t)(m->ctx[0]->rows * m->ctx[0]->shape.groups_pad);
+        const size_t n = (size_t)(m->ctx[0]->rows * m->ctx[0]->shape.groups_pad) * m->ctx[0]->replicas;
         rc = g_nccl.GroupStart();
         for (int d = 0; d < n_devices && rc == 0; ++d)
             rc = g_nccl.AllReduce(m->ctx[d]->d_tally, m->ctx[d]->d_tally, n, kNcclFloat32, kNcclSum, m->comms[d],
@@ -791,7 +807,7 @@ int smk_multi_run(smk_multi *m, double *kernel_seconds, double *total_seconds)
     if (P > 1 && m->allreduce == SMK_ALLREDUCE_PEER) {
         PeerArrays arrays;
         for (int d = 0; d < kMaxDevices; ++d) arrays.p[d] = d < P ? reinterpret_cast<float4 *>(m->ctx[d]->d_tally) : nullptr;
-        const int64_t n4 = m->ctx[0]->rows * m->ctx[0]->shape.groups_pad / 4;
+        const int64_t n4 = m->ctx[0]->rows * m->ctx[0]->shape.groups_pad / 4 * m->ctx[0]->replicas;
         for (int d = 0; d < P; ++d) {
             smk_ctx *c = m->ctx[d];
             SMK_CUDA(cudaSetDevice(c->p.device));
@@ -809,7 +825,7 @@ int smk_multi_run(smk_multi *m, double *kernel_seconds, double *total_seconds)
                 if (e != d) SMK_CUDA(cudaStreamWaitEvent(m->ctx[d]->stream, m->reduced[e], 0));
         }
     } else if (P > 1) {
-        const size_t n = (size_t)(m->ctx[0]->rows * m->ctx[0]->shape.groups_pad);
+        const size_t n = (size_t)(m->ctx[0]->rows * m->ctx[0]->shape.groups_pad) * m->ctx[0]->replicas;
         int rc = g_nccl.GroupStart();
         for (int d = 0; d < P && rc == 0; ++d)
             rc = g_nccl.AllReduce(m->ctx[d]->d_tally, m->ctx[d]->d_tally, n, kNcclFloat32, kNcclSum, m->comms[d],
@@ -860,7 +876,7 @@ void *smk_device_tally(smk_ctx *c) { return c ? c->d_tally : nullptr; }
 void *smk_device_flux0(smk_ctx *c) { return c ? c->d_flux0 : nullptr; }
 void *smk_device_source(smk_ctx *c) { return c ? c->d_source : nullptr; }
 void *smk_device_sigT(smk_ctx *c) { return c ? c->d_sigT : nullptr; }
-int64_t smk_padded_elems(const smk_ctx *c) { return c ? c->rows * c->shape.groups_pad : 0; }
+int64_t smk_padded_elems(const smk_ctx *c) { return c ? c->rows * c->shape.groups_pad * c->replicas : 0; }
 
 void *smk_alloc_host(size_t bytes)
 {

@@ -29,7 +29,9 @@ namespace smk {
 struct KernelArgs {
     const float4 *__restrict__ source;   // [R][F][G_pad/4]
     const float4 *__restrict__ sigT;     // [R][G_pad/4]
-    float *__restrict__ tally;           // [R][F][G_pad]
+    float *__restrict__ tally;           // [replicas][R][F][G_pad]
+    int64_t replica_stride;              // floats between tally replicas (R*F*G_pad)
+    int32_t replicas;                    // >1 for few-row problems: warp w tallies into replica w % replicas
     float *__restrict__ psi_out;         // [tracks in launch][G_pad] or nullptr
     unsigned long long *checksum;        // indexing fingerprint accumulator
     int64_t segments;                    // N
@@ -63,6 +65,15 @@ __device__ __forceinline__ void red_add_v4(float4 *addr, float a, float b, float
                  : "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                  : "memory");
 #endif
+}
+
+// Tally-contention relief (BASELINE config 4: few source regions): when the tally array has few
+// rows, several warps hit the same L2 atomic address at once and serialise there.  The library then
+// keeps `replicas` copies of the (small) array; every warp adds into copy (warp % replicas) and
+// finalize_flux sums the copies.  replicas == 1 for the normal problem sizes.
+__device__ __forceinline__ float *warp_tally(const KernelArgs &a, int64_t warp_global)
+{
+    return a.tally + (a.replicas > 1 ? (warp_global % a.replicas) * a.replica_stride : 0);
 }
 
 __device__ __forceinline__ void prefetch_l1(const void *p)
@@ -138,6 +149,7 @@ attenuate_tracks(const KernelArgs a)
     const int F = a.fai_count;
     const int row_f4 = a.row_f4;
     const int p = a.seg_per_track;
+    float *const tally = warp_tally(a, warp_global);
     unsigned long long checksum = 0ull;
 
     for (int64_t tbase = a.track_begin; tbase < a.track_end; tbase += total_slots) {
@@ -183,7 +195,7 @@ attenuate_tracks(const KernelArgs a)
                 const uint32_t off = row * (uint32_t)row_f4 + (uint32_t)sub;
                 const float4 *src = a.source + off;
                 const float4 *sig = a.sigT + (qsr * (uint32_t)row_f4 + (uint32_t)sub);
-                float4 *tal = reinterpret_cast<float4 *>(a.tally) + off;
+                float4 *tal = reinterpret_cast<float4 *>(tally) + off;
 
                 if constexpr (MATH == kMathFast && LPT == 32) {
                     // one track per warp: the segment type is warp-uniform, so branch on it and
@@ -343,6 +355,7 @@ attenuate_tracks_staged(const KernelArgs a)
     const int p = a.seg_per_track;
     const char *src_bytes = reinterpret_cast<const char *>(a.source);
     const char *sig_bytes = reinterpret_cast<const char *>(a.sigT);
+    float *const tally = warp_tally(a, warp_global);
     unsigned long long checksum = 0ull;
     uint32_t prod_stage = 0, cons_stage = 0, cons_parity = 0;   // ring positions persist across tracks
 
@@ -407,7 +420,7 @@ attenuate_tracks_staged(const KernelArgs a)
 
             const uint32_t packed = __shfl_sync(kFull, cur_packed, s & 31);
             const float4 *stage = reinterpret_cast<const float4 *>(ring + cons_stage * STAGEB);
-            float4 *tal = reinterpret_cast<float4 *>(a.tally) + ((packed & kRowMask) * (uint32_t)ROWF4 + (uint32_t)lane);
+            float4 *tal = reinterpret_cast<float4 *>(tally) + ((packed & kRowMask) * (uint32_t)ROWF4 + (uint32_t)lane);
             mbar_wait(bars_u32 + 8u * cons_stage, cons_parity);
             if (packed & kFlagFirst)
                 segment_staged<NCHUNK, EXPM, kFitFirst>(stage, tal, s_pairs, psi);
@@ -531,6 +544,7 @@ attenuate_tracks_pf(const KernelArgs a)
     const int64_t total_warps = (int64_t)gridDim.x * kWarps;
     const uint32_t F = (uint32_t)a.fai_count;
     const int p = a.seg_per_track;
+    float *const tally = warp_tally(a, warp_global);
     unsigned long long checksum = 0ull;
 
     auto draw = [&](int64_t s0, int idx, int nseg, uint32_t &packed, uint32_t &qsr) {
@@ -588,7 +602,7 @@ attenuate_tracks_pf(const KernelArgs a)
                     load_rows<NCHUNK>(rb, a.source, a.sigT, pb, qb, lane);
                 }
                 compute_by_type<NCHUNK, EXPM>(ra, pa, s_pairs, psi, t);
-                red_row<NCHUNK>(a.tally, pa, lane, t);
+                red_row<NCHUNK>(tally, pa, lane, t);
                 rotate(s);
                 if (s + 1 >= nseg) break;
                 if (s + 2 < nseg) {                                   // request s+2, compute s+1
@@ -596,7 +610,7 @@ attenuate_tracks_pf(const KernelArgs a)
                     load_rows<NCHUNK>(ra, a.source, a.sigT, pa, qa, lane);
                 }
                 compute_by_type<NCHUNK, EXPM>(rb, pb, s_pairs, psi, t);
-                red_row<NCHUNK>(a.tally, pb, lane, t);
+                red_row<NCHUNK>(tally, pb, lane, t);
                 rotate(s + 1);
             }
         } else if constexpr (DEFER) {
@@ -608,12 +622,12 @@ attenuate_tracks_pf(const KernelArgs a)
                 const uint32_t pk = __shfl_sync(kFull, cur_packed, s & 31);
                 const uint32_t qs = __shfl_sync(kFull, cur_qsr, s & 31);
                 load_rows<NCHUNK>(r, a.source, a.sigT, pk, qs, lane);
-                if (s > 0) red_row<NCHUNK>(a.tally, pend, lane, t);
+                if (s > 0) red_row<NCHUNK>(tally, pend, lane, t);
                 compute_by_type<NCHUNK, EXPM>(r, pk, s_pairs, psi, t);
                 pend = pk;
                 rotate(s);
             }
-            if (nseg > 0) red_row<NCHUNK>(a.tally, pend, lane, t);
+            if (nseg > 0) red_row<NCHUNK>(tally, pend, lane, t);
         } else {
             // batches of 32 segments (one id per lane); inside a batch: branch on the warp-uniform
             // segment type first, then load only the rows that type reads, compute, RED
@@ -667,7 +681,7 @@ attenuate_tracks_pf(const KernelArgs a)
                         }
                         compute_rows<NCHUNK, EXPM, kFitInterior>(r, s_pairs, psi, t);
                     }
-                    float4 *tal = reinterpret_cast<float4 *>(a.tally) + off;
+                    float4 *tal = reinterpret_cast<float4 *>(tally) + off;
 #pragma unroll
                     for (int c = 0; c < NCHUNK; ++c) red_add_v4(tal + c * 32, t[c].x, t[c].y, t[c].z, t[c].w);
                 }
@@ -709,14 +723,17 @@ __global__ void pad_rows(const float *__restrict__ src, float *__restrict__ dst,
 
 // out[row][G] = flux0[row][G_pad] + tally[row][G_pad]   (kernel.c:276 summed over the sweep)
 __global__ void finalize_flux(const float *__restrict__ flux0, const float *__restrict__ tally,
-                              float *__restrict__ out, int64_t rows, int groups, int groups_pad)
+                              float *__restrict__ out, int64_t rows, int groups, int groups_pad, int replicas)
 {
     const int64_t n = rows * groups;
+    const int64_t stride = rows * groups_pad;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / groups;
         const int g = (int)(i - r * groups);
-        out[i] = flux0[r * groups_pad + g] + tally[r * groups_pad + g];
+        float t = tally[r * groups_pad + g];
+        for (int k = 1; k < replicas; ++k) t += tally[k * stride + r * groups_pad + g];
+        out[i] = flux0[r * groups_pad + g] + t;
     }
 }
 
