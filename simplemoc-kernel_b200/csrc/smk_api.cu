@@ -205,6 +205,7 @@ struct smk_ctx {
     int64_t psi_capacity;    // in tracks
     int64_t last_begin, last_end;
     unsigned long long *d_checksum;
+    unsigned long long *d_work;  // dynamic track scheduling counter
     cudaStream_t stream;
     bool own_stream;
     cudaEvent_t ev0, ev1;
@@ -353,6 +354,7 @@ int smk_create(const smk_params *p, smk_ctx **out)
     if (e == cudaSuccess) e = cudaMalloc(&c->d_sigT, sig);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_stage, stage);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_checksum, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_work, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) { c->own_stream = true; e = cudaEventCreate(&c->ev0); }
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
@@ -381,6 +383,7 @@ void smk_destroy(smk_ctx *c)
     cudaFree(c->d_stage);
     cudaFree(c->d_psi);
     cudaFree(c->d_checksum);
+    cudaFree(c->d_work);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -499,6 +502,8 @@ static int launch(smk_ctx *c, int64_t track_begin, int64_t track_end)
     a.replicas = c->replicas;
     a.psi_out = (c->p.flags & SMK_FLAG_KEEP_PSI) ? c->d_psi : nullptr;
     a.checksum = c->d_checksum;
+    a.work_counter = c->d_work;
+    SMK_CUDA(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), c->stream));
     a.segments = c->p.segments;
     a.track_begin = track_begin;
     a.track_end = track_end;

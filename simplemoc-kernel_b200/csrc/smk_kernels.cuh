@@ -34,6 +34,7 @@ struct KernelArgs {
     int32_t replicas;                    // >1 for few-row problems: warp w tallies into replica w % replicas
     float *__restrict__ psi_out;         // [tracks in launch][G_pad] or nullptr
     unsigned long long *checksum;        // indexing fingerprint accumulator
+    unsigned long long *work_counter;    // next unclaimed track (relative to track_begin), zeroed per launch
     int64_t segments;                    // N
     int64_t track_begin, track_end;
     uint64_t seed;
@@ -43,9 +44,12 @@ struct KernelArgs {
     int32_t seg_per_track;               // p
 };
 
-constexpr int kThreadsPerBlock = 256;
+#ifndef SMK_THREADS_PER_BLOCK
+#define SMK_THREADS_PER_BLOCK 256
+#endif
+constexpr int kThreadsPerBlock = SMK_THREADS_PER_BLOCK;
 #ifndef SMK_MIN_BLOCKS_FAST
-#define SMK_MIN_BLOCKS_FAST 4
+#define SMK_MIN_BLOCKS_FAST (1024 / SMK_THREADS_PER_BLOCK)
 #endif
 // 4 x 256 threads x 64 registers = the whole register file: 32 warps/SM for the issue-bound FAST kernels
 constexpr int kMinBlocksFast = SMK_MIN_BLOCKS_FAST;
@@ -74,6 +78,17 @@ __device__ __forceinline__ void red_add_v4(float4 *addr, float a, float b, float
 __device__ __forceinline__ float *warp_tally(const KernelArgs &a, int64_t warp_global)
 {
     return a.tally + (a.replicas > 1 ? (warp_global % a.replicas) * a.replica_stride : 0);
+}
+
+// Dynamic track scheduling: warps claim tracks from a global counter instead of striding statically.
+// All CTAs of the persistent grid are resident from the start, so with static striding an SM that runs
+// slower than the others (far L2 partition, fewer co-resident CTAs) sets the kernel time while the fast
+// ones idle: ncu showed 22.5 of 32 warps active on average.  One 64-bit atomic per track (100 segments).
+__device__ __forceinline__ int64_t claim_tracks(const KernelArgs &a, int lane, int n)
+{
+    unsigned long long first = 0ull;
+    if (lane == 0) first = atomicAdd(a.work_counter, (unsigned long long)n);
+    return a.track_begin + (int64_t)__shfl_sync(0xFFFFFFFFu, first, 0);
 }
 
 __device__ __forceinline__ void prefetch_l1(const void *p)
@@ -152,8 +167,9 @@ attenuate_tracks(const KernelArgs a)
     float *const tally = warp_tally(a, warp_global);
     unsigned long long checksum = 0ull;
 
-    for (int64_t tbase = a.track_begin; tbase < a.track_end; tbase += total_slots) {
-        const int64_t track = tbase + slot;
+    for (int64_t tbase = claim_tracks(a, lane, kSlotsPerWarp); tbase < a.track_end;
+         tbase = claim_tracks(a, lane, kSlotsPerWarp)) {
+        const int64_t track = tbase + (lane / LPT);
         const bool tvalid = track < a.track_end;
         const int64_t s0 = track * p;
         int nseg = 0;
@@ -383,7 +399,7 @@ attenuate_tracks_staged(const KernelArgs a)
         bulk_g2s(dst + 3u * ROWB, sig_bytes + (size_t)qsr * ROWB, ROWB, bar);
     };
 
-    for (int64_t track = a.track_begin + warp_global; track < a.track_end; track += total_warps) {
+    for (int64_t track = claim_tracks(a, lane, 1); track < a.track_end; track = claim_tracks(a, lane, 1)) {
         const int64_t s0 = track * p;
         const int64_t left = a.segments - s0;
         const int nseg = left < p ? (int)left : p;
@@ -559,7 +575,7 @@ attenuate_tracks_pf(const KernelArgs a)
         }
     };
 
-    for (int64_t track = a.track_begin + warp_global; track < a.track_end; track += total_warps) {
+    for (int64_t track = claim_tracks(a, lane, 1); track < a.track_end; track = claim_tracks(a, lane, 1)) {
         const int64_t s0 = track * p;
         const int64_t left = a.segments - s0;
         const int nseg = left < p ? (int)left : p;
