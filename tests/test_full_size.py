@@ -77,7 +77,7 @@ def test_full_size_additivity_and_repeatability(smk):
         ctx.reset_tallies()
         ctx.run()
         again = ctx.download_flux().astype(np.float64)
-        assert l2rel(again, full) <= 1e-6                    # only the atomic order differs
+        assert l2rel(again, full) <= 5e-6                    # only the atomic order differs (dynamic scheduling)
         nt = ctx.n_tracks
         ctx.reset_tallies()
         ctx.run(0, nt // 2)
