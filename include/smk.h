@@ -75,6 +75,8 @@ typedef struct smk_params {
 } smk_params;
 
 #define SMK_FLAG_KEEP_PSI  1        /* keep each track's outgoing psi (tests)   */
+#define SMK_FLAG_TALLY_F64 2        /* diagnostic: accumulate the tallies in f64 (order-independent
+                                       yardstick for fp32 accumulation noise; 65..128 groups, FAST) */
 
 typedef struct smk_ctx smk_ctx;     /* opaque: device buffers, stream, events   */
 

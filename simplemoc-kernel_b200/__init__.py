@@ -31,6 +31,7 @@ LIB_PATH = os.environ.get("SMK_LIB") or os.path.join(HERE, "lib", "libsmk.so")
 EXP_POLY, EXP_MUFU, EXP_GLIBC, EXP_TABLE = 0, 1, 2, 3
 MATH_FAST, MATH_STRICT = 0, 1
 FLAG_KEEP_PSI = 1
+FLAG_TALLY_F64 = 2
 
 EXP_MODES = {"poly": EXP_POLY, "mufu": EXP_MUFU, "glibc": EXP_GLIBC, "table": EXP_TABLE}
 MATH_MODES = {"fast": MATH_FAST, "strict": MATH_STRICT}
@@ -162,6 +163,7 @@ class Input:
     exp_mode: str = "poly"
     math_mode: str = "fast"
     device: int = 0
+    tally_f64: bool = False              # diagnostic: f64 tally accumulators (SMK_FLAG_TALLY_F64)
 
     def finalize(self) -> "Input":
         """main.c:18-19: source_3D_regions = ceil(2D * coarse / decomp)."""
@@ -176,6 +178,8 @@ class Input:
     def params(self, flags: int = 0) -> Params:
         if self.source_3D_regions == 0:
             self.finalize()
+        if self.tally_f64:
+            flags |= FLAG_TALLY_F64
         return Params(self.source_3D_regions, self.fine_axial_intervals, self.egroups,
                       self.seg_per_thread, self.segments, self.seed, EXP_MODES[self.exp_mode],
                       MATH_MODES[self.math_mode], self.device, flags)

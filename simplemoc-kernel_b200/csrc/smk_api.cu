@@ -206,6 +206,7 @@ struct smk_ctx {
     int64_t last_begin, last_end;
     unsigned long long *d_checksum;
     unsigned long long *d_work;  // dynamic track scheduling counter
+    double *d_tally64;           // SMK_FLAG_TALLY_F64: f64 tally accumulators, [R][F][G_pad]
     cudaStream_t stream;
     bool own_stream;
     cudaEvent_t ev0, ev1;
@@ -316,6 +317,13 @@ int smk_create(const smk_params *p, smk_ctx **out)
         return fail(SMK_EINVAL, "no kernel for egroups=%d math=%d exp=%d", p->egroups, p->math_mode,
                     p->exp_mode);
     }
+    if (p->flags & SMK_FLAG_TALLY_F64) {
+        // the f64 accumulators are only wired into the flat one-track-per-warp kernel
+        if (c->kernel != pick_flat(shape, p->math_mode, p->exp_mode, false)) {
+            delete c;
+            return fail(SMK_EINVAL, "SMK_FLAG_TALLY_F64 needs 65..128 groups, FAST math and the default kernel");
+        }
+    }
     c->rows = (int64_t)p->source_3D_regions * p->fine_axial_intervals;
     // few tally rows => L2 atomics on the same addresses serialise: spread them over replicas so that
     // at least ~4096 rows are in play (1 for the reference's default 33750 rows)
@@ -355,6 +363,10 @@ int smk_create(const smk_params *p, smk_ctx **out)
     if (e == cudaSuccess) e = cudaMalloc(&c->d_stage, stage);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_checksum, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_work, sizeof(unsigned long long));
+    if (e == cudaSuccess && (p->flags & SMK_FLAG_TALLY_F64)) {
+        e = cudaMalloc(&c->d_tally64, 2 * slab);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tally64, 0, 2 * slab, c->stream);
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) { c->own_stream = true; e = cudaEventCreate(&c->ev0); }
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
@@ -384,6 +396,7 @@ void smk_destroy(smk_ctx *c)
     cudaFree(c->d_psi);
     cudaFree(c->d_checksum);
     cudaFree(c->d_work);
+    cudaFree(c->d_tally64);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -429,6 +442,8 @@ int smk_reset_tallies(smk_ctx *c)
     SMK_CUDA(cudaMemsetAsync(c->d_tally, 0, (size_t)c->rows * c->shape.groups_pad * sizeof(float) * c->replicas,
                              c->stream));
     SMK_CUDA(cudaMemsetAsync(c->d_checksum, 0, sizeof(unsigned long long), c->stream));
+    if (c->d_tally64)
+        SMK_CUDA(cudaMemsetAsync(c->d_tally64, 0, (size_t)c->rows * c->shape.groups_pad * sizeof(double), c->stream));
     return SMK_OK;
 }
 
@@ -503,6 +518,7 @@ static int launch(smk_ctx *c, int64_t track_begin, int64_t track_end)
     a.psi_out = (c->p.flags & SMK_FLAG_KEEP_PSI) ? c->d_psi : nullptr;
     a.checksum = c->d_checksum;
     a.work_counter = c->d_work;
+    a.tally64 = c->d_tally64;
     SMK_CUDA(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), c->stream));
     a.segments = c->p.segments;
     a.track_begin = track_begin;
@@ -560,8 +576,11 @@ int smk_download_flux(smk_ctx *c, float *out)
     if (!c || !out) return fail(SMK_EINVAL, "NULL argument");
     SMK_CUDA(cudaSetDevice(c->p.device));
     const int G = c->p.egroups, Gp = c->shape.groups_pad;
-    finalize_flux<<<layout_grid(c->rows * G), 256, 0, c->stream>>>(c->d_flux0, c->d_tally, c->d_stage, c->rows, G, Gp,
-                                                                 c->replicas);
+    if (c->d_tally64)
+        finalize_flux64<<<layout_grid(c->rows * G), 256, 0, c->stream>>>(c->d_flux0, c->d_tally64, c->d_stage, c->rows, G, Gp);
+    else
+        finalize_flux<<<layout_grid(c->rows * G), 256, 0, c->stream>>>(c->d_flux0, c->d_tally, c->d_stage, c->rows, G, Gp,
+                                                                     c->replicas);
     SMK_CUDA(cudaGetLastError());
     c->launches += 1;
     SMK_CUDA(cudaMemcpyAsync(out, c->d_stage, (size_t)c->rows * G * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -651,7 +670,7 @@ struct Nccl {
     }
 };
 Nccl g_nccl;
-constexpr int kNcclFloat32 = 7, kNcclSum = 0;   // ncclFloat32, ncclSum (nccl.h)
+constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0;   // ncclFloat32, ncclFloat64, ncclSum (nccl.h)
 }  // namespace
 
 struct smk_multi {
@@ -810,16 +829,22 @@ int smk_multi_run(smk_multi *m, double *kernel_seconds, double *total_seconds)
     }
     // 2. one all-reduce of the tally deltas
     if (P > 1 && m->allreduce == SMK_ALLREDUCE_PEER) {
+        const bool f64 = m->ctx[0]->d_tally64 != nullptr;
         PeerArrays arrays;
-        for (int d = 0; d < kMaxDevices; ++d) arrays.p[d] = d < P ? reinterpret_cast<float4 *>(m->ctx[d]->d_tally) : nullptr;
-        const int64_t n4 = m->ctx[0]->rows * m->ctx[0]->shape.groups_pad / 4 * m->ctx[0]->replicas;
+        for (int d = 0; d < kMaxDevices; ++d)
+            arrays.p[d] = d < P ? (f64 ? reinterpret_cast<float4 *>(m->ctx[d]->d_tally64)
+                                       : reinterpret_cast<float4 *>(m->ctx[d]->d_tally)) : nullptr;
+        // elements per device array: float4 for the fp32 tallies, double for the f64 diagnostic ones
+        const int64_t n4 = f64 ? m->ctx[0]->rows * m->ctx[0]->shape.groups_pad
+                               : m->ctx[0]->rows * m->ctx[0]->shape.groups_pad / 4 * m->ctx[0]->replicas;
         for (int d = 0; d < P; ++d) {
             smk_ctx *c = m->ctx[d];
             SMK_CUDA(cudaSetDevice(c->p.device));
             for (int e = 0; e < P; ++e)
                 if (e != d) SMK_CUDA(cudaStreamWaitEvent(c->stream, m->swept[e], 0));
             const int64_t b = d * n4 / P, e4 = (d + 1) * n4 / P;
-            allreduce_peer_slices<<<layout_grid(e4 - b), 256, 0, c->stream>>>(arrays, P, b, e4);
+            if (f64) allreduce_peer_slices64<<<layout_grid(e4 - b), 256, 0, c->stream>>>(arrays, P, b, e4);
+            else allreduce_peer_slices<<<layout_grid(e4 - b), 256, 0, c->stream>>>(arrays, P, b, e4);
             SMK_CUDA(cudaGetLastError());
             c->launches += 1;
             SMK_CUDA(cudaEventRecord(m->reduced[d], c->stream));
@@ -830,11 +855,14 @@ int smk_multi_run(smk_multi *m, double *kernel_seconds, double *total_seconds)
                 if (e != d) SMK_CUDA(cudaStreamWaitEvent(m->ctx[d]->stream, m->reduced[e], 0));
         }
     } else if (P > 1) {
-        const size_t n = (size_t)(m->ctx[0]->rows * m->ctx[0]->shape.groups_pad) * m->ctx[0]->replicas;
+        const bool f64 = m->ctx[0]->d_tally64 != nullptr;
+        const size_t n = f64 ? (size_t)(m->ctx[0]->rows * m->ctx[0]->shape.groups_pad)
+                             : (size_t)(m->ctx[0]->rows * m->ctx[0]->shape.groups_pad) * m->ctx[0]->replicas;
         int rc = g_nccl.GroupStart();
-        for (int d = 0; d < P && rc == 0; ++d)
-            rc = g_nccl.AllReduce(m->ctx[d]->d_tally, m->ctx[d]->d_tally, n, kNcclFloat32, kNcclSum, m->comms[d],
-                                  m->ctx[d]->stream);
+        for (int d = 0; d < P && rc == 0; ++d) {
+            void *buf = f64 ? (void *)m->ctx[d]->d_tally64 : (void *)m->ctx[d]->d_tally;
+            rc = g_nccl.AllReduce(buf, buf, n, f64 ? kNcclFloat64 : kNcclFloat32, kNcclSum, m->comms[d], m->ctx[d]->stream);
+        }
         if (rc == 0) rc = g_nccl.GroupEnd();
         if (rc != 0) return fail(SMK_ECUDA, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
     }

@@ -35,6 +35,7 @@ struct KernelArgs {
     float *__restrict__ psi_out;         // [tracks in launch][G_pad] or nullptr
     unsigned long long *checksum;        // indexing fingerprint accumulator
     unsigned long long *work_counter;    // next unclaimed track (relative to track_begin), zeroed per launch
+    double *tally64;                     // diagnostic: f64 tally accumulators [R][F][G_pad] (SMK_FLAG_TALLY_F64)
     int64_t segments;                    // N
     int64_t track_begin, track_end;
     uint64_t seed;
@@ -89,6 +90,15 @@ __device__ __forceinline__ int64_t claim_tracks(const KernelArgs &a, int lane, i
     unsigned long long first = 0ull;
     if (lane == 0) first = atomicAdd(a.work_counter, (unsigned long long)n);
     return a.track_begin + (int64_t)__shfl_sync(0xFFFFFFFFu, first, 0);
+}
+
+// diagnostic f64 tallies: order-independent to ~1e-16, the yardstick for fp32 accumulation noise
+__device__ __forceinline__ void red_add_f64x4(double *addr, float a, float b, float c, float d)
+{
+    asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(addr), "d"((double)a) : "memory");
+    asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(addr + 1), "d"((double)b) : "memory");
+    asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(addr + 2), "d"((double)c) : "memory");
+    asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(addr + 3), "d"((double)d) : "memory");
 }
 
 __device__ __forceinline__ void prefetch_l1(const void *p)
@@ -697,9 +707,15 @@ attenuate_tracks_pf(const KernelArgs a)
                         }
                         compute_rows<NCHUNK, EXPM, kFitInterior>(r, s_pairs, psi, t);
                     }
-                    float4 *tal = reinterpret_cast<float4 *>(tally) + off;
+                    if (a.tally64 == nullptr) {
+                        float4 *tal = reinterpret_cast<float4 *>(tally) + off;
 #pragma unroll
-                    for (int c = 0; c < NCHUNK; ++c) red_add_v4(tal + c * 32, t[c].x, t[c].y, t[c].z, t[c].w);
+                        for (int c = 0; c < NCHUNK; ++c) red_add_v4(tal + c * 32, t[c].x, t[c].y, t[c].z, t[c].w);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < NCHUNK; ++c)
+                            red_add_f64x4(a.tally64 + ((size_t)off + c * 32) * 4, t[c].x, t[c].y, t[c].z, t[c].w);
+                    }
                 }
                 cur_packed = nxt_packed;
                 cur_qsr = nxt_qsr;
@@ -796,6 +812,29 @@ __global__ void allreduce_peer_slices(PeerArrays arrays, int n_dev, int64_t begi
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
         for (int d = 0; d < n_dev; ++d) arrays.p[d][i] = acc;
+    }
+}
+
+// out[row][G] = (float)(flux0 + tally64): finalize for the diagnostic f64 tallies
+__global__ void finalize_flux64(const float *__restrict__ flux0, const double *__restrict__ tally64,
+                                float *__restrict__ out, int64_t rows, int groups, int groups_pad)
+{
+    const int64_t n = rows * groups;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / groups;
+        const int g = (int)(i - r * groups);
+        out[i] = (float)((double)flux0[r * groups_pad + g] + tally64[r * groups_pad + g]);
+    }
+}
+
+__global__ void allreduce_peer_slices64(PeerArrays arrays, int n_dev, int64_t begin, int64_t end)
+{
+    for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double acc = reinterpret_cast<double *>(arrays.p[0])[i];
+        for (int d = 1; d < n_dev; ++d) acc += reinterpret_cast<double *>(arrays.p[d])[i];
+        for (int d = 0; d < n_dev; ++d) reinterpret_cast<double *>(arrays.p[d])[i] = acc;
     }
 }
 

@@ -37,6 +37,7 @@ typedef struct {
     unsigned long long seed;
     int exp_mode, math_mode, device, gpus, allreduce;
     int host_fill;
+    int tally_f64;
     float sigt_floor;
     const char *dump_flux;
     const char *verify_flux;   /* raw float32 flux of a CPU replay of the same stream */
@@ -109,6 +110,7 @@ static void usage_and_exit(void)
     puts("  --gpus <n>            Split the segments over n GPUs, all-reduce the tallies");
     puts("  --allreduce <impl>    peer (NVLink peer-memory kernel, default) | nccl");
     puts("  --host-fill           Fill the slabs on the host and upload them");
+    puts("  --tally-f64           Diagnostic: accumulate the tallies in double precision");
     puts("  --sigt-floor <x>      Well-conditioned diagnostic data: sigT in [x, 1)");
     puts("  --dump-flux <file>    Write the final scalar flux (raw float32)");
     puts("  --verify <file>       Compare the flux with a CPU replay of the same stream (raw float32,");
@@ -169,6 +171,7 @@ static void parse(int argc, char **argv, Input *I)
         else if (!strcmp(a, "--gpus")) I->gpus = atoi(need(argc, argv, &i));
         else if (!strcmp(a, "--allreduce")) I->allreduce = lookup(need(argc, argv, &i), reduces, 2);
         else if (!strcmp(a, "--host-fill")) I->host_fill = 1;
+        else if (!strcmp(a, "--tally-f64")) I->tally_f64 = 1;
         else if (!strcmp(a, "--sigt-floor")) I->sigt_floor = (float)atof(need(argc, argv, &i));
         else if (!strcmp(a, "--dump-flux")) I->dump_flux = need(argc, argv, &i);
         else if (!strcmp(a, "--verify")) I->verify_flux = need(argc, argv, &i);
@@ -275,6 +278,7 @@ int main(int argc, char *argv[])
     p.exp_mode = I.exp_mode;
     p.math_mode = I.math_mode;
     p.device = I.device;
+    p.flags = I.tally_f64 ? SMK_FLAG_TALLY_F64 : 0;
 
     smk_ctx *ctx = NULL;
     smk_multi *multi = NULL;

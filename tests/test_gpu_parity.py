@@ -340,3 +340,24 @@ def test_fast_mode_across_seeds_default_geometry(smk, oracle, seed):
     assert chk == chk_want
     assert np.array_equal(np.isfinite(flux), np.isfinite(want))
     assert l2rel(flux, want) <= TOL_FAST
+
+
+def test_f64_tally_diagnostic(smk, oracle):
+    """SMK_FLAG_TALLY_F64: with double-precision accumulators the result no longer depends on the order
+    of the additions, so (a) it matches the oracle's f64-accumulated replay, (b) sharded sweeps add up to
+    the full sweep essentially exactly -- the yardstick for fp32 accumulation noise at scale."""
+    R, F, G, N, p, seed = 14, 5, 128, 400_000, 100, 71          # few regions: deep accumulation
+    src, flux0, sig = oracle.fill(R, F, G, seed)
+    want64 = flux0.copy()
+    oracle.run(src, want64, sig, N, p, seed, nthreads=0, flags=2)
+    I = make_input(smk, R, F, G, N, p, seed)
+    I.tally_f64 = True
+    full, _, _ = gpu_run(smk, I, src, flux0, sig)
+    assert l2rel(full, want64) <= 2e-6                          # FAST arithmetic only, no accumulation noise
+    nt = (N + p - 1) // p
+    zero = np.zeros_like(flux0)
+    parts = [gpu_run(smk, I, src, zero, sig, tb=k * nt // 3, te=(k + 1) * nt // 3)[0].astype(np.float64) for k in range(3)]
+    assert l2rel(flux0 + sum(parts), full) <= 3e-7              # float32 rounding of the downloads only
+    I.egroups = 64
+    with pytest.raises(smk.SmkError):                           # only wired into the 65..128-group kernel
+        smk.Context(I)
