@@ -46,7 +46,9 @@ SMK_HD void mulhilo(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo)
 SMK_HD u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                            uint32_t k0, uint32_t k1)
 {
+#if defined(__CUDA_ARCH__)
 #pragma unroll
+#endif
     for (int r = 0; r < 10; ++r) {
         uint32_t hi0, lo0, hi1, lo1;
         mulhilo(kPhiloxM0, c0, hi0, lo0);
