@@ -168,8 +168,6 @@ attenuate_tracks(const KernelArgs a)
     const int lane = threadIdx.x & 31;
     const int sub = lane & (LPT - 1);               // lane within its track
     const int64_t warp_global = (int64_t)blockIdx.x * (kThreadsPerBlock / 32) + (threadIdx.x >> 5);
-    const int64_t total_slots = (int64_t)gridDim.x * (kThreadsPerBlock / 32) * kSlotsPerWarp;
-    const int64_t slot = warp_global * kSlotsPerWarp + (lane / LPT);
 
     const int F = a.fai_count;
     const int row_f4 = a.row_f4;
@@ -376,7 +374,6 @@ attenuate_tracks_staged(const KernelArgs a)
     __syncthreads();
 
     const int64_t warp_global = (int64_t)blockIdx.x * kWarps + warp;
-    const int64_t total_warps = (int64_t)gridDim.x * kWarps;
     const uint32_t F = (uint32_t)a.fai_count;
     const int p = a.seg_per_track;
     const char *src_bytes = reinterpret_cast<const char *>(a.source);
@@ -567,7 +564,6 @@ attenuate_tracks_pf(const KernelArgs a)
     }
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
-    const int64_t total_warps = (int64_t)gridDim.x * kWarps;
     const uint32_t F = (uint32_t)a.fai_count;
     const int p = a.seg_per_track;
     float *const tally = warp_tally(a, warp_global);
