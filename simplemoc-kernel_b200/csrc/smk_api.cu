@@ -524,6 +524,7 @@ static int launch(smk_ctx *c, int64_t track_begin, int64_t track_end)
     a.track_begin = track_begin;
     a.track_end = track_end;
     a.seed = c->p.seed;
+    a.keys = make_philox_keys(c->p.seed);
     a.mod_regions = make_fastmod((uint32_t)c->p.source_3D_regions);
     a.mod_fai = make_fastmod((uint32_t)c->p.fine_axial_intervals);
     a.fai_count = c->p.fine_axial_intervals;

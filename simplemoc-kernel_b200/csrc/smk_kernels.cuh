@@ -39,6 +39,7 @@ struct KernelArgs {
     int64_t segments;                    // N
     int64_t track_begin, track_end;
     uint64_t seed;
+    PhiloxKeys keys;                     // expanded Philox key schedule of `seed`
     FastMod mod_regions, mod_fai;
     int32_t fai_count;                   // F
     int32_t row_f4;                      // G_pad / 4: float4 per row
@@ -190,7 +191,7 @@ attenuate_tracks(const KernelArgs a)
         float4 psi[NCHUNK];
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c) {
-            const u32x4 w = stream_words(a.seed, (uint64_t)track, (uint32_t)(c * LPT + sub), kDomainPsi);
+            const u32x4 w = stream_words(a.keys, (uint64_t)track, (uint32_t)(c * LPT + sub), kDomainPsi);
             psi[c] = make_float4(u01(w.x), u01(w.y), u01(w.z), u01(w.w));
         }
 
@@ -201,7 +202,7 @@ attenuate_tracks(const KernelArgs a)
             uint32_t my_qsr = 0u, my_fai = 0u;
             if (b + sub < nseg) {
                 const uint64_t seg = (uint64_t)(s0 + b + sub);
-                const SegmentIds id = segment_ids(a.seed, seg, a.mod_regions, a.mod_fai);
+                const SegmentIds id = segment_ids(a.keys, seg, a.mod_regions, a.mod_fai);
                 my_qsr = id.qsr;
                 my_fai = id.fai;
                 checksum += checksum_term(id.qsr, id.fai, (uint32_t)F, seg);
@@ -388,7 +389,7 @@ attenuate_tracks_staged(const KernelArgs a)
         qsr = 0u;
         if (idx < nseg) {
             const uint64_t seg = (uint64_t)(s0 + idx);
-            const SegmentIds id = segment_ids(a.seed, seg, a.mod_regions, a.mod_fai);
+            const SegmentIds id = segment_ids(a.keys, seg, a.mod_regions, a.mod_fai);
             checksum += checksum_term(id.qsr, id.fai, F, seg);
             qsr = id.qsr;
             packed = (id.qsr * F + id.fai) | (id.fai == 0u ? kFlagFirst : 0u) | (id.fai == F - 1u ? kFlagLast : 0u);
@@ -414,7 +415,7 @@ attenuate_tracks_staged(const KernelArgs a)
         float4 psi[NCHUNK];
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c) {
-            const u32x4 w = stream_words(a.seed, (uint64_t)track, (uint32_t)(c * 32 + lane), kDomainPsi);
+            const u32x4 w = stream_words(a.keys, (uint64_t)track, (uint32_t)(c * 32 + lane), kDomainPsi);
             psi[c] = make_float4(u01(w.x), u01(w.y), u01(w.z), u01(w.w));
         }
 
@@ -574,7 +575,7 @@ attenuate_tracks_pf(const KernelArgs a)
         qsr = 0u;
         if (idx < nseg) {
             const uint64_t seg = (uint64_t)(s0 + idx);
-            const SegmentIds id = segment_ids(a.seed, seg, a.mod_regions, a.mod_fai);
+            const SegmentIds id = segment_ids(a.keys, seg, a.mod_regions, a.mod_fai);
             checksum += checksum_term(id.qsr, id.fai, F, seg);
             qsr = id.qsr;
             packed = (id.qsr * F + id.fai) | (id.fai == 0u ? kFlagFirst : 0u) | (id.fai == F - 1u ? kFlagLast : 0u);
@@ -589,7 +590,7 @@ attenuate_tracks_pf(const KernelArgs a)
         float4 psi[NCHUNK];
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c) {
-            const u32x4 w = stream_words(a.seed, (uint64_t)track, (uint32_t)(c * 32 + lane), kDomainPsi);
+            const u32x4 w = stream_words(a.keys, (uint64_t)track, (uint32_t)(c * 32 + lane), kDomainPsi);
             psi[c] = make_float4(u01(w.x), u01(w.y), u01(w.z), u01(w.w));
         }
 

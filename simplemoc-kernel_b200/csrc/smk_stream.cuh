@@ -62,6 +62,47 @@ SMK_HD u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
     return u32x4{c0, c1, c2, c3};
 }
 
+// The key schedule (k0 + r W0, k1 + r W1), r = 0..9, only depends on the seed: the host expands it once
+// and the kernels read the 20 words straight from the constant bank (kernel parameters), which removes
+// two integer adds per round from every hash.
+struct PhiloxKeys {
+    uint32_t k[20];
+};
+
+inline PhiloxKeys make_philox_keys(uint64_t seed)
+{
+    PhiloxKeys ks;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        ks.k[2 * r] = k0;
+        ks.k[2 * r + 1] = k1;
+        k0 += kPhiloxW0;
+        k1 += kPhiloxW1;
+    }
+    return ks;
+}
+
+SMK_HD u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys &ks)
+{
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo(kPhiloxM0, c0, hi0, lo0);
+        mulhilo(kPhiloxM1, c2, hi1, lo1);
+        uint32_t n0 = hi1 ^ c1 ^ ks.k[2 * r];
+        uint32_t n2 = hi0 ^ c3 ^ ks.k[2 * r + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    return u32x4{c0, c1, c2, c3};
+}
+
+SMK_HD u32x4 stream_words(const PhiloxKeys &ks, uint64_t index, uint32_t sub, uint32_t domain)
+{
+    return philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), sub, domain, ks);
+}
+
 SMK_HD u32x4 stream_words(uint64_t seed, uint64_t index, uint32_t sub, uint32_t domain)
 {
     return philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), sub, domain,
@@ -104,6 +145,13 @@ SMK_HD uint32_t fastmod(uint32_t n, const FastMod &f)  // n < 2^31
 }
 
 struct SegmentIds { uint32_t qsr, fai; };
+
+SMK_HD SegmentIds segment_ids(const PhiloxKeys &ks, uint64_t seg, const FastMod &mod_regions,
+                              const FastMod &mod_fai)
+{
+    u32x4 w = stream_words(ks, seg, 0u, kDomainSegment);
+    return SegmentIds{fastmod(w.x >> 1, mod_regions), fastmod(w.y >> 1, mod_fai)};
+}
 
 SMK_HD SegmentIds segment_ids(uint64_t seed, uint64_t seg, const FastMod &mod_regions,
                               const FastMod &mod_fai)
