@@ -27,7 +27,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "segment x energy-group intersections/s"
+METRIC = "segment\u00d7energy-group intersections/sec"   # BASELINE.json metric
 UNIT = "intersections/s"
 # 10.4 B source rows (2.6 rows avg) + 4 B sigT + 4 B tally RED payload
 ALGO_BYTES_PER_INTERSECTION = 18.4
