@@ -55,6 +55,10 @@ constexpr int kThreadsPerBlock = SMK_THREADS_PER_BLOCK;
 #endif
 // 4 x 256 threads x 64 registers = the whole register file: 32 warps/SM for the issue-bound FAST kernels
 constexpr int kMinBlocksFast = SMK_MIN_BLOCKS_FAST;
+#ifndef SMK_UNROLL_K
+#define SMK_UNROLL_K 1
+#endif
+constexpr int kUnrollSegments = SMK_UNROLL_K;   // unroll factor of the per-segment loop of the flat kernel
 #ifndef SMK_MIN_BLOCKS_PREFETCH
 #define SMK_MIN_BLOCKS_PREFETCH 3
 #endif
@@ -656,6 +660,7 @@ attenuate_tracks_pf(const KernelArgs a)
             // segment type first, then load only the rows that type reads, compute, RED
             for (int b = 0; b < nseg; b += 32) {
                 const int count = (nseg - b) < 32 ? (nseg - b) : 32;
+#pragma unroll(kUnrollSegments)
                 for (int k = 0; k < count; ++k) {
                     const uint32_t pk = __shfl_sync(kFull, cur_packed, k);
                     const uint32_t qs = __shfl_sync(kFull, cur_qsr, k);
