@@ -361,3 +361,18 @@ def test_f64_tally_diagnostic(smk, oracle):
     I.egroups = 64
     with pytest.raises(smk.SmkError):                           # only wired into the 65..128-group kernel
         smk.Context(I)
+
+
+def test_unmodified_reference_driver_runs_on_libsmk():
+    """Link-time drop-in: the reference's own main.c / init.c / io.c, unmodified,
+    linked against libsmk.so through host/run_kernel_shim.c (built into oracle/_ref while /root/reference
+    was mounted).  Its own banner, input summary and timing printout around a sweep that ran on the GPU."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "SimpleMOC-kernel_refmain_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/SimpleMOC-kernel_refmain_gpu not built (needs /root/reference at build time)")
+    r = subprocess.run([exe, "-s", "5000000", "-e", "128", "-t", "2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for line in ("INPUT SUMMARY", "Energy Groups:            128", "Segments:                 5,000,000",
+                 "Attentuating fluxes across segments...", "GPU sweep:", "Simulation Complete.", "Runtime:",
+                 "Time per Intersection:"):
+        assert line in r.stdout, line
