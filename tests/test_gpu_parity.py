@@ -372,7 +372,7 @@ def test_unmodified_reference_driver_runs_on_libsmk():
         pytest.skip("oracle/_ref/SimpleMOC-kernel_refmain_gpu not built (needs /root/reference at build time)")
     r = subprocess.run([exe, "-s", "5000000", "-e", "128", "-t", "2"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    for line in ("INPUT SUMMARY", "Energy Groups:            128", "Segments:                 5,000,000",
+    for line in ("INPUT SUMMARY", f"{'Energy Groups:':<25}128", f"{'Segments:':<25}5,000,000",
                  "Attentuating fluxes across segments...", "GPU sweep:", "Simulation Complete.", "Runtime:",
                  "Time per Intersection:"):
         assert line in r.stdout, line
