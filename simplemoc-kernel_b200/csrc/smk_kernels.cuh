@@ -1,12 +1,18 @@
 // smk_kernels.cuh -- sm_100a kernels of the segment-attenuation path.
 //
-//   attenuate_tracks<LPT, NCHUNK, MATH, EXPM>   the hot kernel: run_kernel's segment
-//       loop + attenuate_segment (/root/reference/src/cpu/kernel.c:43-55, 75-333)
+//   attenuate_tracks_pf<NCHUNK, EXPM, ...>       the hot kernel for 65..128 energy groups (default "flat"
+//       variant; "prefetch", "defer", "l1pf" are measured alternatives): run_kernel's segment loop +
+//       attenuate_segment (/root/reference/src/cpu/kernel.c:43-55, 75-333), one warp per track
+//   attenuate_tracks<LPT, NCHUNK, MATH, EXPM>    the general kernel: every other group count (sub-warp
+//       tracks, several float4 per lane) and the STRICT verification arithmetic
+//   attenuate_tracks_staged<NCHUNK, EXPM, STAGES> measured alternative: rows staged through shared memory
+//       by TMA bulk copies (cp.async.bulk + mbarrier ring)
 //   fill_rows                                    device-side deterministic fill
 //       (replaces /root/reference/src/cpu/init.c:64-75 + the H2D of init.cu:105-127)
-//   pad_rows / finalize_flux                     host layout <-> padded device layout
+//   pad_rows / finalize_flux[64]                 host layout <-> padded device layout
+//   allreduce_peer_slices[64]                    multi-GPU all-reduce of the tallies over NVLink peer memory
 //
-// Work decomposition of the hot kernel
+// Work decomposition of the hot kernels
 //   track  = seg_per_track consecutive segments sharing one carried angular flux psi
 //   a track is owned by LPT lanes of one warp (LPT = lanes per track, a power of two);
 //   each lane owns NCHUNK float4 = 4*NCHUNK energy groups and keeps their psi in
@@ -14,9 +20,11 @@
 //   track, 128-bit loads, one 16-byte vector RED per lane per segment);
 //   G = 64 -> LPT = 16 (2 tracks per warp); G = 7 -> G_pad = 8, LPT = 2 (16 tracks
 //   per warp, the 8th group is padding).
+//   Warps claim tracks dynamically from a global counter (claim_tracks).
 //   Segment ids come from the counter stream: every LPT segments each lane of the
 //   track hashes ONE upcoming segment and the ids are handed round with shuffles, so
 //   the Philox cost per intersection is 1/(4*NCHUNK*LPT) of a hash.
+//   The FAST arithmetic is packed FP32x2 (FFMA2/FMUL2/FADD2), see smk_math.cuh.
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
@@ -53,7 +61,7 @@ constexpr int kThreadsPerBlock = SMK_THREADS_PER_BLOCK;
 #ifndef SMK_MIN_BLOCKS_FAST
 #define SMK_MIN_BLOCKS_FAST (1024 / SMK_THREADS_PER_BLOCK)
 #endif
-// 4 x 256 threads x 64 registers = the whole register file: 32 warps/SM for the issue-bound FAST kernels
+// 4 x 256 threads x 64 registers = the whole register file: 32 warps/SM for the FAST kernels
 constexpr int kMinBlocksFast = SMK_MIN_BLOCKS_FAST;
 #ifndef SMK_UNROLL_K
 #define SMK_UNROLL_K 1
