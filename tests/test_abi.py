@@ -106,3 +106,23 @@ def test_product_does_not_touch_the_oracle():
     out = subprocess.run(["ldd", os.path.join(ROOT, "simplemoc-kernel_b200", "lib", "libsmk.so")],
                          capture_output=True, text=True).stdout
     assert "oracle" not in out and "libref" not in out
+
+
+def test_multi_and_misc_argument_validation(smk):
+    """Argument errors are reported (negative code + message), never a crash, before any CUDA work."""
+    h = C.c_void_p()
+    p = smk.Params(10, 5, 8, 10, 100, 1, 0, 0, 0, 0)
+    assert smk.lib.smk_multi_create(C.byref(p), 0, None, 0, C.byref(h)) == -1
+    assert smk.lib.smk_multi_create(C.byref(p), 9, None, 0, C.byref(h)) == -1
+    assert smk.lib.smk_multi_create(C.byref(p), 2, None, 7, C.byref(h)) == -1
+    assert smk.lib.smk_multi_create(None, 2, None, 0, C.byref(h)) == -1
+    assert smk.lib.smk_upload(None, None, None, None) == -1
+    assert smk.lib.smk_run(None, 0, 0, None) == -1
+    assert smk.lib.smk_download_flux(None, None) == -1
+    assert smk.lib.smk_multi_run(None, None, None) == -1
+    assert smk.lib.smk_launch_count(None) == 0
+    assert smk.lib.smk_padded_elems(None) == 0
+    smk.lib.smk_destroy(None)          # no-ops
+    smk.lib.smk_multi_destroy(None)
+    smk.lib.smk_free_host(None)
+    assert smk.lib.smk_last_error()
