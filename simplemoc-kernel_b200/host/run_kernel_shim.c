@@ -10,8 +10,9 @@
  *       /root/reference/src/cpu/{main,init,io}.c simplemoc-kernel_b200/host/run_kernel_shim.c \
  *       -Lsimplemoc-kernel_b200/lib -lsmk -lm -o SimpleMOC-kernel
  *
- * (oracle/Makefile builds exactly this into oracle/_ref/ while /root/reference is mounted; the reference
- * header is taken from there at build time, nothing of it is copied here.)  The reference's main() then
+ * (The repository's reference-build recipe builds exactly this while /root/reference is mounted, see
+ * INTEGRATION.md section 1; the reference header is taken from there at build time, nothing of it is
+ * copied here.)  The reference's main() then
  * prints its own banner, input summary and "Time per Intersection" around a sweep that ran on the GPU;
  * its timer brackets the whole call (main.c:45-47), i.e. context creation, H2D, sweep and D2H.
  *
