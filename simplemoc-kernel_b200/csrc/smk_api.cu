@@ -162,8 +162,21 @@ static AttenuateFn pick_pf_exp(int expm)
 
 // flat-loop kernels for the one-track-per-warp shapes, FAST math: "flat" (loads at use) and
 // "prefetch" (software-pipelined through a second register set)
+static AttenuateFn pick_half(int expm)
+{
+    switch (expm) {
+        case kExpPoly: return attenuate_tracks_half<kExpPoly>;
+        case kExpMufu: return attenuate_tracks_half<kExpMufu>;
+        case kExpGlibc: return attenuate_tracks_half<kExpGlibc>;
+        case kExpTable: return attenuate_tracks_half<kExpTable>;
+    }
+    return nullptr;
+}
+
 static AttenuateFn pick_flat(const Shape &s, int math, int expm, bool prefetch, bool defer = false, bool l1pf = false)
 {
+    // 33..64 groups (G_pad = 64): one track per warp with two groups per lane
+    if (math == kMathFast && s.lpt == 16 && s.nchunk == 1 && !prefetch && !defer && !l1pf) return pick_half(expm);
     if (math != kMathFast || s.lpt != 32) return nullptr;
     if (l1pf) return s.nchunk == 1 ? pick_pf_exp<1, false, false, true>(expm) : nullptr;
     if (defer) return s.nchunk == 1 ? pick_pf_exp<1, false, true>(expm) : nullptr;
@@ -319,7 +332,7 @@ int smk_create(const smk_params *p, smk_ctx **out)
     }
     if (p->flags & SMK_FLAG_TALLY_F64) {
         // the f64 accumulators are only wired into the flat one-track-per-warp kernel
-        if (c->kernel != pick_flat(shape, p->math_mode, p->exp_mode, false)) {
+        if (shape.lpt != 32 || c->kernel != pick_flat(shape, p->math_mode, p->exp_mode, false)) {
             delete c;
             return fail(SMK_EINVAL, "SMK_FLAG_TALLY_F64 needs 65..128 groups, FAST math and the default kernel");
         }

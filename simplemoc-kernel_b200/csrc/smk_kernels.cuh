@@ -746,6 +746,102 @@ attenuate_tracks_pf(const KernelArgs a)
 }
 
 // ------------------------------------------------------------------------------
+// attenuate_tracks_half<EXPM>: the flat one-track-per-warp kernel for 33..64 energy groups
+// (G_pad = 64): each lane owns TWO groups (one packed FP32x2 pair), 64-bit loads, one 8-byte vector
+// RED per lane per segment.  Compared with the general kernel (two tracks per warp, per-lane fit
+// coefficients) the segment type is warp-uniform again, so the edge bodies skip the quadratic terms.
+// ------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v2(float2 *addr, float a, float b)
+{
+    asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+template <int EXPM>
+__global__ void __launch_bounds__(kThreadsPerBlock, kMinBlocksFast)
+attenuate_tracks_half(const KernelArgs a)
+{
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    constexpr int kWarps = kThreadsPerBlock / 32;
+    constexpr uint32_t ROWF2 = 32;                         // float2 per padded row (G_pad = 64)
+
+    __shared__ float2 s_pairs[kTableReach];
+    if constexpr (EXPM == kExpTable) {
+        if (threadIdx.x < kTableReach) s_pairs[threadIdx.x] = c_exp_table.pairs[threadIdx.x];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const uint32_t F = (uint32_t)a.fai_count;
+    const int p = a.seg_per_track;
+    const float2 *const source = reinterpret_cast<const float2 *>(a.source);
+    const float2 *const sigT = reinterpret_cast<const float2 *>(a.sigT);
+    float2 *const tally = reinterpret_cast<float2 *>(warp_tally(a, warp_global));
+    unsigned long long checksum = 0ull;
+
+    auto draw = [&](int64_t s0, int idx, int nseg, uint32_t &packed, uint32_t &qsr) {
+        packed = 0u;
+        qsr = 0u;
+        if (idx < nseg) {
+            const uint64_t seg = (uint64_t)(s0 + idx);
+            const SegmentIds id = segment_ids(a.keys, seg, a.mod_regions, a.mod_fai);
+            checksum += checksum_term(id.qsr, id.fai, F, seg);
+            qsr = id.qsr;
+            packed = (id.qsr * F + id.fai) | (id.fai == 0u ? kFlagFirst : 0u) | (id.fai == F - 1u ? kFlagLast : 0u);
+        }
+    };
+
+    for (int64_t track = claim_tracks(a, lane, 1); track < a.track_end; track = claim_tracks(a, lane, 1)) {
+        const int64_t s0 = track * p;
+        const int64_t left = a.segments - s0;
+        const int nseg = left < p ? (int)left : p;
+
+        // psi0: one Philox block covers 4 groups = the two groups of lanes 2j and 2j+1
+        const u32x4 w = stream_words(a.keys, (uint64_t)track, (uint32_t)(lane >> 1), kDomainPsi);
+        float2 psi = (lane & 1) ? make_float2(u01(w.z), u01(w.w)) : make_float2(u01(w.x), u01(w.y));
+
+        uint32_t cur_packed, cur_qsr, nxt_packed, nxt_qsr;
+        draw(s0, lane, nseg, cur_packed, cur_qsr);
+        draw(s0, 32 + lane, nseg, nxt_packed, nxt_qsr);
+
+        for (int b = 0; b < nseg; b += 32) {
+            const int count = (nseg - b) < 32 ? (nseg - b) : 32;
+            for (int k = 0; k < count; ++k) {
+                const uint32_t pk = __shfl_sync(kFull, cur_packed, k);
+                const uint32_t qs = __shfl_sync(kFull, cur_qsr, k);
+                const uint32_t off = (pk & kRowMask) * ROWF2 + (uint32_t)lane;
+                const float2 *src = source + off;
+                const float2 st = __ldg(sigT + (qs * ROWF2 + (uint32_t)lane));
+                const float2 y2 = __ldg(src);
+                const float2 zero = make_float2(0.f, 0.f);
+                float2 t;
+                if (pk & kFlagFirst) {
+                    const float2 y3 = __ldg(src + ROWF2);
+                    attenuate_fast2<EXPM, kFitFirst>(FitCoeffs{}, zero, y2, y3, st, s_pairs, psi, t);
+                } else if (pk & kFlagLast) {
+                    const float2 y1 = __ldg(src - ROWF2);
+                    attenuate_fast2<EXPM, kFitLast>(FitCoeffs{}, y1, y2, zero, st, s_pairs, psi, t);
+                } else {
+                    const float2 y1 = __ldg(src - ROWF2);
+                    const float2 y3 = __ldg(src + ROWF2);
+                    attenuate_fast2<EXPM, kFitInterior>(FitCoeffs{}, y1, y2, y3, st, s_pairs, psi, t);
+                }
+                red_add_v2(tally + off, t.x, t.y);                                  // kernel.c:276
+            }
+            cur_packed = nxt_packed;
+            cur_qsr = nxt_qsr;
+            draw(s0, b + 64 + lane, nseg, nxt_packed, nxt_qsr);
+        }
+
+        if (a.psi_out != nullptr)
+            reinterpret_cast<float2 *>(a.psi_out)[(track - a.track_begin) * ROWF2 + lane] = psi;
+    }
+
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) checksum += __shfl_xor_sync(kFull, checksum, off);
+    if (lane == 0 && checksum != 0ull) atomicAdd(a.checksum, checksum);
+}
+
+// ------------------------------------------------------------------------------
 // layout kernels
 // ------------------------------------------------------------------------------
 

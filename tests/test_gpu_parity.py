@@ -124,6 +124,8 @@ CASES = [
     (50,  5, 128, 10_000,  100, 2**63 + 12345),   # 64-bit seed (both Philox key words in use)
     (50,  5, 128, 6_400,   64,  17),    # track length = two id batches exactly
     (50,  5, 128, 6_500,   65,  18),    # track length = two id batches + 1
+    (80,  5, 40,  40_000,  100, 19),    # 33..64 groups: one track per warp, two groups per lane, 24 padded
+    (80,  5, 64,  40_033,  70,  20),    # same kernel, full rows, ragged last track
 ]
 
 
