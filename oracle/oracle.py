@@ -23,6 +23,17 @@ REF_DIR = os.path.join(HERE, "_ref")
 
 TABLE = 1
 F64ACC = 2
+GEOM = 4        # per-segment geometry from stream words 2,3 (kernel.c:95-104)
+
+# kernel.c:99-104: dz, zin, weight, mu, mu2, ds (+ spread of the per-segment variation)
+REFERENCE_GEOMETRY = (0.1, 0.3, 0.5, 0.9, 0.3, 0.7)
+
+
+def geometry7(base=REFERENCE_GEOMETRY, spread=0.0) -> np.ndarray:
+    """{dz, zin, weight, mu, mu2, ds, spread} as the float32 vector the C side takes."""
+    g = np.array(list(base) + [spread], np.float32)
+    assert g.shape == (7,)
+    return g
 
 _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -73,6 +84,12 @@ class Oracle:
                                      _f32p, _f32p, _f32p, C.c_int64, C.c_int64, C.c_void_p,
                                      C.POINTER(C.c_uint64), C.c_int, C.c_uint]
         L.smk_oracle_run.restype = C.c_int
+        L.smk_oracle_run_geom.argtypes = L.smk_oracle_run.argtypes + [C.c_void_p]
+        L.smk_oracle_run_geom.restype = C.c_int
+        L.smk_oracle_segment_geometry.argtypes = [C.c_uint64, C.c_int64, C.c_int64, _f32p, _f32p]
+        L.smk_oracle_segment_geometry.restype = None
+        L.smk_oracle_attenuate_segment_geom.argtypes = L.smk_oracle_attenuate_segment.argtypes + [_f32p]
+        L.smk_oracle_attenuate_segment_geom.restype = None
         L.smk_oracle_max_threads.restype = C.c_int
 
     # -- stream -------------------------------------------------------------
@@ -121,29 +138,40 @@ class Oracle:
         return out
 
     # -- math ---------------------------------------------------------------
-    def attenuate_segment(self, fai_id, src_region, sigt_region, psi, use_table=False):
-        """src_region [F][G], sigt_region [G], psi [G] (updated in place). Returns tally [G]."""
+    def attenuate_segment(self, fai_id, src_region, sigt_region, psi, use_table=False, geom6=None):
+        """src_region [F][G], sigt_region [G], psi [G] (updated in place). Returns tally [G].
+        geom6 = (dz, zin, weight, mu, mu2, ds) overrides the constants of kernel.c:99-104."""
         fai_count, groups = src_region.shape
         tally = np.zeros(groups, np.float32)
-        self.lib.smk_oracle_attenuate_segment(groups, fai_count, fai_id,
-                                              np.ascontiguousarray(src_region, np.float32),
-                                              np.ascontiguousarray(sigt_region, np.float32),
-                                              psi, tally, int(use_table))
+        args = (groups, fai_count, fai_id, np.ascontiguousarray(src_region, np.float32),
+                np.ascontiguousarray(sigt_region, np.float32), psi, tally, int(use_table))
+        if geom6 is None:
+            self.lib.smk_oracle_attenuate_segment(*args)
+        else:
+            self.lib.smk_oracle_attenuate_segment_geom(*args, np.asarray(geom6, np.float32))
         return tally
 
+    def segment_geometry(self, seed, seg_begin, count, geom7):
+        """(count, 6) array of dz, zin, weight, mu, mu2, ds of each segment."""
+        out = np.zeros((count, 6), np.float32)
+        self.lib.smk_oracle_segment_geometry(seed, seg_begin, count, np.asarray(geom7, np.float32), out)
+        return out
+
     def run(self, src, flux, sig, segments, seg_per_track, seed, track_begin=0, track_end=None,
-            want_psi=False, nthreads=0, flags=0):
+            want_psi=False, nthreads=0, flags=0, geom7=None):
         """Replays tracks [track_begin, track_end); flux is updated IN PLACE.
-        Returns (psi_final or None, id_checksum)."""
+        Returns (psi_final or None, id_checksum).  geom7 (see geometry7()) replaces the constants of
+        kernel.c:99-104; with flags & GEOM they additionally vary per segment."""
         regions, fai, groups = src.shape
         nt = n_tracks(segments, seg_per_track)
         track_end = nt if track_end is None else track_end
         psi = np.zeros((track_end - track_begin, groups), np.float32) if want_psi else None
         chk = C.c_uint64(0)
-        rc = self.lib.smk_oracle_run(regions, fai, groups, segments, seg_per_track, seed,
-                                     src, flux, sig, track_begin, track_end,
-                                     psi.ctypes.data if want_psi else None, C.byref(chk),
-                                     nthreads, flags)
+        g7 = None if geom7 is None else np.ascontiguousarray(geom7, np.float32)
+        rc = self.lib.smk_oracle_run_geom(regions, fai, groups, segments, seg_per_track, seed,
+                                          src, flux, sig, track_begin, track_end,
+                                          psi.ctypes.data if want_psi else None, C.byref(chk),
+                                          nthreads, flags, None if g7 is None else g7.ctypes.data)
         if rc != 0:
             raise ValueError(f"smk_oracle_run rejected its arguments (code {rc})")
         return psi, chk.value

@@ -3,7 +3,7 @@
  *
  * TEST INFRASTRUCTURE ONLY (see oracle/smk_oracle.c header).
  *
- * oracle/build.sh compiles this file together with
+ * oracle/Makefile (target `ref`) compiles this file together with
  *   /root/reference/src/cpu/kernel.c and /root/reference/src/cpu/init.c
  * (from where they lie; nothing is copied into this repo) into oracle/_ref/*.so.
  * It feeds the reference's own attenuate_segment (kernel.c:75-333, an external

@@ -17,10 +17,10 @@
  * here independently of the CUDA implementation.
  *
  * Parity pin: the reference has no golden vectors, so this
- * restatement is pinned against the reference's own object code: oracle/build.sh
- * compiles the unmodified /root/reference/src/cpu/{kernel.c,init.c} into
- * oracle/_ref/ and tests/test_oracle_vs_reference.py checks that this file and
- * the reference's attenuate_segment agree BIT FOR BIT on the same stream (exp and
+ * restatement is pinned against the reference's own object code: oracle/Makefile
+ * (target `ref`) compiles the unmodified /root/reference/src/cpu/{kernel.c,init.c}
+ * into oracle/_ref/ and tests/test_oracle.py checks that this file and the
+ * reference's attenuate_segment agree BIT FOR BIT on the same stream (exp and
  * table builds).  Fixtures produced by that reference build are committed under
  * tests/golden/ so the pin also holds where /root/reference is absent.
  * The Philox generator is pinned against the Random123 known-answer vectors.
@@ -85,8 +85,8 @@ static inline void stream_words(uint64_t seed, uint64_t index, uint32_t sub,
 }
 
 /* (QSR_id, FAI_id) of global segment `seg`; `%` as in kernel.c:47,50 on a
- * 31-bit draw (rand_r's range).  Words 2,3 are reserved for per-segment
- * geometry (kernel.c:95-104 says the full app derives ds, mu, ... per segment). */
+ * 31-bit draw (rand_r's range).  Words 2,3 carry the per-segment geometry
+ * (segment_geometry below; kernel.c:95-104). */
 void smk_oracle_segment_ids(uint64_t seed, int64_t seg_begin, int64_t count,
                             int regions, int fai, int32_t *qsr_out,
                             int32_t *fai_out)
@@ -137,6 +137,68 @@ void smk_oracle_fill(float *fine_source, float *fine_flux, float *sigT,
     if (fine_source) fill_array(fine_source, n, 0u, seed, 0.0f);
     if (fine_flux)   fill_array(fine_flux, n, 1u, seed, 0.0f);
     if (sigT)        fill_array(sigT, (int64_t)regions * groups, 2u, seed, sigt_floor);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Segment geometry.  kernel.c:95-104: "Some placeholder constants - In the    */
+/* full app some of these are calculated based off position in geometry."      */
+/* The six placeholders become parameters; with SMK_ORACLE_GEOM they vary per  */
+/* segment, drawn from words 2,3 of the segment's stream block (DESIGN.md      */
+/* section 3b): four 16-bit fields u -> factor f(u) = 1 + spread*(u*2^-15 - 1) */
+/*   ds = ds0 f(w2>>16)   zin = zin0 f(w2&0xFFFF)   mu = mu0 f(w3>>16)         */
+/*   mu2 = mu2_0 f(w3>>16)^2   weight = weight0 f(w3&0xFFFF)   dz = dz0        */
+/* (dz is a property of the axial mesh, the same for every segment).  Every    */
+/* operation is a single IEEE binary32 operation in the order written, so the  */
+/* GPU reproduces the values bit for bit; spread = 0 gives f = 1 exactly, i.e.  */
+/* the base values, i.e. the reference when the base is kernel.c:99-104.        */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    float dz, zin, weight, mu, mu2, ds;
+} seg_geometry;
+
+static const seg_geometry k_reference_geometry = { /* kernel.c:99-104 */
+    0.1f, 0.3f, 0.5f, 0.9f, 0.3f, 0.7f
+};
+
+static inline float geom_factor(uint32_t u16, float spread)
+{
+    const float t = (float)u16 * 0x1.0p-15f; /* exact */
+    const float c = t - 1.0f;                /* exact: <= 16 significant bits */
+    const float sc = spread * c;
+    return 1.0f + sc;
+}
+
+/* base[7] = { dz, zin, weight, mu, mu2, ds, spread } */
+static inline seg_geometry segment_geometry(const float *base, uint32_t w2, uint32_t w3)
+{
+    seg_geometry g;
+    const float spread = base[6];
+    const float f_ds = geom_factor(w2 >> 16, spread);
+    const float f_zin = geom_factor(w2 & 0xFFFFu, spread);
+    const float f_mu = geom_factor(w3 >> 16, spread);
+    const float f_w = geom_factor(w3 & 0xFFFFu, spread);
+    const float f_mu_sq = f_mu * f_mu;
+    g.dz = base[0];
+    g.zin = base[1] * f_zin;
+    g.weight = base[2] * f_w;
+    g.mu = base[3] * f_mu;
+    g.mu2 = base[4] * f_mu_sq;
+    g.ds = base[5] * f_ds;
+    return g;
+}
+
+/* geometry of segments [seg_begin, seg_begin + count): out[i*6 + {0..5}] =
+ * dz, zin, weight, mu, mu2, ds (for tests of the GPU's derivation) */
+void smk_oracle_segment_geometry(uint64_t seed, int64_t seg_begin, int64_t count,
+                                 const float *base7, float *out)
+{
+    for (int64_t i = 0; i < count; i++) {
+        uint32_t w[4];
+        stream_words(seed, (uint64_t)(seg_begin + i), 0u, DOMAIN_SEGMENT, w);
+        const seg_geometry g = segment_geometry(base7, w[2], w[3]);
+        out[i * 6 + 0] = g.dz; out[i * 6 + 1] = g.zin; out[i * 6 + 2] = g.weight;
+        out[i * 6 + 3] = g.mu; out[i * 6 + 4] = g.mu2; out[i * 6 + 5] = g.ds;
+    }
 }
 
 /* ------------------------------------------------------------------------- */
@@ -205,14 +267,15 @@ static void attenuate_one_segment(int groups, int fai_count, int FAI_id,
                                   const float *src_region, /* [F][G] */
                                   const float *sigT_region, /* [G]    */
                                   float *psi, float *tally,
-                                  const oracle_table *table)
+                                  const oracle_table *table,
+                                  const seg_geometry *geom)
 {
-    const float dz = 0.1f;       /* kernel.c:99-104 */
-    const float zin = 0.3f;
-    const float weight = 0.5f;
-    const float mu = 0.9f;
-    const float mu2 = 0.3f;
-    const float ds = 0.7f;
+    const float dz = geom->dz;   /* kernel.c:99-104, as parameters */
+    const float zin = geom->zin;
+    const float weight = geom->weight;
+    const float mu = geom->mu;
+    const float mu2 = geom->mu2;
+    const float ds = geom->ds;
 
     const float *f1 = src_region + (int64_t)(FAI_id - 1) * groups;
     const float *f2 = src_region + (int64_t)FAI_id * groups;
@@ -288,7 +351,23 @@ void smk_oracle_attenuate_segment(int groups, int fai_count, int FAI_id,
     if (use_table)
         t.N = smk_oracle_build_table(0.01f, 10.0f, tv, 706, &t.dx, &t.maxVal);
     attenuate_one_segment(groups, fai_count, FAI_id, src_region, sigT_region,
-                          psi, tally_out, use_table ? &t : NULL);
+                          psi, tally_out, use_table ? &t : NULL, &k_reference_geometry);
+}
+
+/* Same with caller-supplied geometry geom6 = { dz, zin, weight, mu, mu2, ds }. */
+void smk_oracle_attenuate_segment_geom(int groups, int fai_count, int FAI_id,
+                                       const float *src_region,
+                                       const float *sigT_region, float *psi,
+                                       float *tally_out, int use_table,
+                                       const float *geom6)
+{
+    float tv[706];
+    oracle_table t = { tv, 0.f, 0.f, 0 };
+    if (use_table)
+        t.N = smk_oracle_build_table(0.01f, 10.0f, tv, 706, &t.dx, &t.maxVal);
+    const seg_geometry g = { geom6[0], geom6[1], geom6[2], geom6[3], geom6[4], geom6[5] };
+    attenuate_one_segment(groups, fai_count, FAI_id, src_region, sigT_region,
+                          psi, tally_out, use_table ? &t : NULL, &g);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -299,17 +378,21 @@ void smk_oracle_attenuate_segment(int groups, int fai_count, int FAI_id,
 /* ------------------------------------------------------------------------- */
 #define SMK_ORACLE_TABLE   1u  /* use the interpolation table (TABLE build)   */
 #define SMK_ORACLE_F64ACC  2u  /* diagnostic: accumulate tallies in double    */
+#define SMK_ORACLE_GEOM    4u  /* per-segment geometry from stream words 2,3  */
 
 /* Returns 0 on success.  fine_flux is updated in place (kernel.c:274-277).
  * psi_final, if non-NULL, receives the outgoing psi of each track in
  * [track_begin, track_end): psi_final[(t - track_begin)*groups + g].
  * id_checksum, if non-NULL, receives sum over segments of
  * (QSR_id*fai + FAI_id + 1) * ((seg & 0xFFFF) + 1) mod 2^64 (indexing fingerprint). */
-int smk_oracle_run(int regions, int fai, int groups, int64_t segments,
-                   int seg_per_track, uint64_t seed,
-                   const float *fine_source, float *fine_flux, const float *sigT,
-                   int64_t track_begin, int64_t track_end, float *psi_final,
-                   uint64_t *id_checksum, int nthreads, unsigned flags)
+/* geom7 = { dz, zin, weight, mu, mu2, ds, spread } or NULL for kernel.c:99-104.
+ * Without SMK_ORACLE_GEOM every segment uses the base values (spread ignored). */
+int smk_oracle_run_geom(int regions, int fai, int groups, int64_t segments,
+                        int seg_per_track, uint64_t seed,
+                        const float *fine_source, float *fine_flux, const float *sigT,
+                        int64_t track_begin, int64_t track_end, float *psi_final,
+                        uint64_t *id_checksum, int nthreads, unsigned flags,
+                        const float *geom7)
 {
     if (regions < 1 || fai < 2 || groups < 1 || seg_per_track < 1 || segments < 0)
         return 1;
@@ -322,6 +405,13 @@ int smk_oracle_run(int regions, int fai, int groups, int64_t segments,
     const int use_table = (flags & SMK_ORACLE_TABLE) != 0;
     if (use_table)
         tab.N = smk_oracle_build_table(0.01f, 10.0f, tv, 706, &tab.dx, &tab.maxVal);
+
+    float base7[7] = { k_reference_geometry.dz, k_reference_geometry.zin,
+                       k_reference_geometry.weight, k_reference_geometry.mu,
+                       k_reference_geometry.mu2, k_reference_geometry.ds, 0.0f };
+    if (geom7) memcpy(base7, geom7, sizeof base7);
+    const int per_segment = (flags & SMK_ORACLE_GEOM) != 0;
+    const seg_geometry fixed = { base7[0], base7[1], base7[2], base7[3], base7[4], base7[5] };
 
     const int64_t rows = (int64_t)regions * fai;
     double *acc64 = NULL;
@@ -354,15 +444,18 @@ int smk_oracle_run(int regions, int fai, int groups, int64_t segments,
             int64_t s1 = s0 + seg_per_track;
             if (s1 > segments) s1 = segments;
             for (int64_t s = s0; s < s1; s++) {
-                int32_t QSR_id, FAI_id;
-                smk_oracle_segment_ids(seed, s, 1, regions, fai, &QSR_id, &FAI_id);
+                uint32_t w[4];
+                stream_words(seed, (uint64_t)s, 0u, DOMAIN_SEGMENT, w);
+                const int32_t QSR_id = (int32_t)((w[0] >> 1) % (uint32_t)regions); /* kernel.c:47 */
+                const int32_t FAI_id = (int32_t)((w[1] >> 1) % (uint32_t)fai);     /* kernel.c:50 */
                 checksum += ((uint64_t)QSR_id * (uint64_t)fai + (uint64_t)FAI_id + 1u)
                             * ((uint64_t)(s & 0xFFFF) + 1u);
+                const seg_geometry g = per_segment ? segment_geometry(base7, w[2], w[3]) : fixed;
 
                 attenuate_one_segment(groups, fai, FAI_id,
                                       fine_source + (int64_t)QSR_id * fai * groups,
                                       sigT + (int64_t)QSR_id * groups, psi, tally,
-                                      use_table ? &tab : NULL);
+                                      use_table ? &tab : NULL, &g);
 
                 const int64_t row = (int64_t)QSR_id * fai + FAI_id;
                 if (acc64) {
@@ -403,6 +496,17 @@ int smk_oracle_run(int regions, int fai, int groups, int64_t segments,
 #endif
     if (id_checksum) *id_checksum = checksum;
     return 0;
+}
+
+int smk_oracle_run(int regions, int fai, int groups, int64_t segments,
+                   int seg_per_track, uint64_t seed,
+                   const float *fine_source, float *fine_flux, const float *sigT,
+                   int64_t track_begin, int64_t track_end, float *psi_final,
+                   uint64_t *id_checksum, int nthreads, unsigned flags)
+{
+    return smk_oracle_run_geom(regions, fai, groups, segments, seg_per_track, seed,
+                               fine_source, fine_flux, sigT, track_begin, track_end,
+                               psi_final, id_checksum, nthreads, flags, NULL);
 }
 
 int smk_oracle_max_threads(void)

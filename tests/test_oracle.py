@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle.oracle import F64ACC, TABLE, Oracle, Reference
+from oracle.oracle import F64ACC, GEOM, REFERENCE_GEOMETRY, TABLE, Oracle, Reference, geometry7
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 
@@ -162,3 +162,94 @@ def test_rejects_bad_arguments(oracle):
     before = flux.copy()
     oracle.run(src, flux, sig, 0, 10, 1)
     assert np.array_equal(before, flux)
+
+
+# ---------------------------------------------------------------------------------------
+# per-segment geometry (kernel.c:95-104 made parameters)
+# ---------------------------------------------------------------------------------------
+def test_geometry_draws(oracle):
+    """Four 16-bit fields of stream words 2,3 -> factors in [1-spread, 1+spread); dz is global."""
+    g7 = geometry7(spread=0.25)
+    g = oracle.segment_geometry(42, 0, 100_000, g7)
+    base = np.array(REFERENCE_GEOMETRY, np.float32)
+    assert (g[:, 0] == base[0]).all()                                   # dz
+    for col in (1, 2, 3, 5):                                            # zin, weight, mu, ds
+        f = g[:, col].astype(np.float64) / base[col]
+        assert f.min() >= 0.75 - 1e-6 and f.max() < 1.25 + 1e-6 and abs(f.mean() - 1.0) < 5e-3
+    f_mu = g[:, 3].astype(np.float64) / base[3]
+    assert np.allclose(g[:, 4], base[4] * f_mu ** 2, rtol=3e-7)        # mu2 follows mu^2
+    # zin and ds come from different halves of one word, mu and weight of the other: uncorrelated
+    assert abs(np.corrcoef(g[:, 1], g[:, 5])[0, 1]) < 0.02 and abs(np.corrcoef(g[:, 3], g[:, 2])[0, 1]) < 0.02
+    # counter-based: a sub-range replays identically; spread = 0 is the base, exactly
+    assert np.array_equal(bits(oracle.segment_geometry(42, 777, 50, g7)), bits(g[777:827]))
+    g0 = oracle.segment_geometry(42, 0, 1000, geometry7(spread=0.0))
+    assert np.array_equal(bits(g0), bits(np.tile(base, (1000, 1))))
+
+
+@pytest.mark.skipif(not Reference.available("strict"), reason="oracle/_ref not built")
+def test_geometry_constant_point_vs_reference_object_code(oracle):
+    """Pin (i): the parametrised restatement, driven through its per-segment path but with the draws
+    mapped onto the constants (spread = 0), is bit-identical to the unmodified kernel.c."""
+    ref = Reference("strict")
+    R, F, G, N, p, seed = 30, 5, 100, 9000, 100, 77
+    src, flux0, sig = oracle.fill(R, F, G, seed)
+    b = flux0.copy()
+    psi_b = ref.replay(src, b, sig, N, p, seed, want_psi=True)
+    a = flux0.copy()
+    psi_a, _ = oracle.run(src, a, sig, N, p, seed, want_psi=True, nthreads=1, flags=GEOM,
+                          geom7=geometry7(spread=0.0))
+    assert np.array_equal(bits(a), bits(b)) and np.array_equal(bits(psi_a), bits(psi_b))
+    # Power-of-two gauge: (dz, zin, mu, mu2) -> (2 dz, 2 zin, 2 mu, 4 mu2) leaves q0, q1 mu and q2 mu2
+    # unchanged in exact binary arithmetic (c1 halves, c2 quarters, kernel.c:182-189), so a restatement
+    # that uses every parameter where kernel.c uses its constant reproduces the reference bit for bit;
+    # doubling the weight doubles every tally exactly (kernel.c:262).
+    dz, zin, w, mu, mu2, ds = REFERENCE_GEOMETRY
+    c = np.zeros_like(flux0)
+    psi_c, _ = oracle.run(src, c, sig, N, p, seed, want_psi=True, nthreads=1, flags=GEOM,
+                          geom7=geometry7((2 * dz, 2 * zin, 2 * w, 2 * mu, 4 * mu2, ds), 0.0))
+    d = np.zeros_like(flux0)
+    ref.replay(src, d, sig, N, p, seed)                                 # reference tallies on zero flux
+    assert np.array_equal(bits(psi_c), bits(psi_b))
+    assert np.array_equal(bits(c), bits(np.float32(2.0) * d))
+
+
+def test_geometry_known_answer_in_double(oracle):
+    """One interior and one edge segment with a non-reference geometry against the formulae of
+    SURVEY.md section 3.3 evaluated in double precision."""
+    rng = np.random.default_rng(5)
+    src = rng.random((5, 8)).astype(np.float32)
+    sig = (0.3 + 0.7 * rng.random(8)).astype(np.float32)
+    dz, zin, w, mu, mu2, ds = 0.2, 0.05, 0.8, 0.6, 0.36, 0.45
+    for fai in (2, 0, 4):
+        psi0 = rng.random(8).astype(np.float32)
+        psi = psi0.copy()
+        tally = oracle.attenuate_segment(fai, src, sig, psi, geom6=(dz, zin, w, mu, mu2, ds))
+        y1, y2, y3 = (src[min(max(fai + k, 0), 4)].astype(np.float64) for k in (-1, 0, 1))
+        if fai == 0:
+            c1, c2 = (y3 - y2) / dz, 0.0
+        elif fai == 4:
+            c1, c2 = (y2 - y1) / dz, 0.0
+        else:
+            c1, c2 = (y1 - y3) / (2 * dz), (y1 - 2 * y2 + y3) / (2 * dz * dz)
+        q0, q1, q2 = y2 + c1 * zin + c2 * zin * zin, c1 + 2 * c2 * zin, c2
+        s = sig.astype(np.float64)
+        tau = s * ds
+        ev = 1 - np.exp(-tau)
+        reuse = tau * (tau - 2) + 2 * ev / s ** 3
+        fi = ((q0 * tau + (s * psi0 - q0) * ev) / s ** 2 + q1 * mu * reuse
+              + q2 * mu2 * (tau * (tau * (tau - 3) + 6) - 6 * ev) / (3 * s ** 4))
+        pso = q0 * ev / s + q1 * mu * (tau - ev) / s ** 2 + q2 * mu2 * reuse + psi0 * (1 - ev)
+        assert np.allclose(tally, w * fi, rtol=2e-4, atol=1e-5)
+        assert np.allclose(psi, pso, rtol=2e-4, atol=1e-5)
+
+
+def test_geometry_spread_changes_results_smoothly(oracle):
+    """With per-segment draws the sweep differs from the constant one by O(spread), same indexing."""
+    R, F, G, N, p, seed = 20, 5, 32, 20_000, 100, 9
+    src, flux0, sig = oracle.fill(R, F, G, seed, 0.1)
+    a, b, c = flux0.copy(), flux0.copy(), flux0.copy()
+    _, chk_a = oracle.run(src, a, sig, N, p, seed, nthreads=1)
+    _, chk_b = oracle.run(src, b, sig, N, p, seed, nthreads=1, flags=GEOM, geom7=geometry7(spread=0.01))
+    _, chk_c = oracle.run(src, c, sig, N, p, seed, nthreads=1, flags=GEOM, geom7=geometry7(spread=0.3))
+    assert chk_a == chk_b == chk_c
+    assert 0 < l2rel(b, a) < 0.01 and 5 * l2rel(b, a) < l2rel(c, a) < 0.5      # zero-mean draws average out over a sweep
