@@ -18,7 +18,8 @@
  *   - host arrays use the reference's unpadded layouts (init.c:35-54):
  *         fine_source[R][F][G], fine_flux[R][F][G], sigT[R][G]   (float)
  *     with R = source_3D_regions, F = fine_axial_intervals, G = egroups.
- *   - device arrays are padded to G_pad groups per row (smk_padded_groups()).
+ *   - device arrays are padded to G_pad groups per row (smk_padded_groups()); any
+ *     G >= 1 is supported (rows wider than 256 groups are swept in blocks of 256).
  *   - a "track" is seg_per_track consecutive segments of the deterministic
  *     stream that share one carried angular flux.
  */
@@ -32,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SMK_ABI_VERSION 1
+#define SMK_ABI_VERSION 2
 
 /* error codes */
 #define SMK_OK          0
@@ -43,7 +44,13 @@ extern "C" {
 
 /* how 1 - exp(-tau) is evaluated (kernel.c:216-223) */
 #define SMK_EXP_POLY    0   /* FMA-pipe polynomial, correctly rounded where the
-                               reference formula is ill-conditioned (default)  */
+                               reference formula is ill-conditioned (default).
+                               Domain: the polynomial is fitted for tau = sigT*ds
+                               <= 0.7 (the reference's own data: sigT < 1, ds =
+                               0.7).  The library tracks max(sigT) of the uploaded
+                               data; when max(sigT) * max(ds) > 0.7 it switches to
+                               a form that evaluates tau > 0.7 with MUFU.EX2 (well
+                               conditioned there), so any non-negative sigT is safe */
 #define SMK_EXP_MUFU    1   /* MUFU.EX2 (ex2.approx.ftz), 2 ulp                 */
 #define SMK_EXP_GLIBC   2   /* double-precision replica of glibc 2.39 expf      */
 #define SMK_EXP_TABLE   3   /* the reference's interpolation table
@@ -76,7 +83,25 @@ typedef struct smk_params {
 
 #define SMK_FLAG_KEEP_PSI  1        /* keep each track's outgoing psi (tests)   */
 #define SMK_FLAG_TALLY_F64 2        /* diagnostic: accumulate the tallies in f64 (order-independent
-                                       yardstick for fp32 accumulation noise; 65..128 groups, FAST) */
+                                       yardstick for fp32 accumulation noise); every kernel */
+#define SMK_FLAG_SEGMENT_GEOMETRY 4 /* dz, zin, weight, mu, mu2, ds of kernel.c:99-104 vary per segment
+                                       (smk_geometry / smk_set_geometry below)  */
+
+/*
+ * Segment geometry.  /root/reference/src/cpu/kernel.c:95-104: "Some placeholder constants - In the
+ * full app some of these are calculated based off position in geometry."  With
+ * SMK_FLAG_SEGMENT_GEOMETRY the six placeholders are parameters and vary per segment: words 2,3 of
+ * the segment's stream block give four 16-bit fields u, each mapped to a factor
+ * f(u) = 1 + spread * (u * 2^-15 - 1) in [1 - spread, 1 + spread):
+ *     ds = ds0 f(w2 >> 16)    zin = zin0 f(w2 & 0xFFFF)    mu = mu0 f(w3 >> 16)
+ *     mu2 = mu2_0 f(w3 >> 16)^2    weight = weight0 f(w3 & 0xFFFF)    dz = dz0 (axial mesh)
+ * every step one IEEE binary32 operation, replayed identically by the CPU
+ * oracle.  spread = 0 reproduces the base values exactly; base = kernel.c:99-104 is the default.
+ */
+typedef struct smk_geometry {
+    float dz, zin, weight, mu, mu2, ds;   /* base values; defaults 0.1 0.3 0.5 0.9 0.3 0.7 */
+    float spread;                         /* in [0, 1); default 0.25                        */
+} smk_geometry;
 
 typedef struct smk_ctx smk_ctx;     /* opaque: device buffers, stream, events   */
 
@@ -97,12 +122,35 @@ int   smk_create(const smk_params *p, smk_ctx **out);
 void  smk_destroy(smk_ctx *ctx);
 /* run on a caller-owned cudaStream_t (passed as void*) instead of the context's */
 int   smk_set_stream(smk_ctx *ctx, void *cuda_stream);
+/* base values and spread of the per-segment geometry; the context must have been created
+ * with SMK_FLAG_SEGMENT_GEOMETRY (SMK_ESTATE otherwise).  dz, ds > 0, 0 <= spread < 1. */
+int   smk_set_geometry(smk_ctx *ctx, const smk_geometry *g);
+int   smk_get_geometry(const smk_ctx *ctx, smk_geometry *g);
+/* name of the kernel instantiation the next smk_run will launch, e.g.
+ * "attenuate_warp_track<4 groups/lane, poly, f32 tally, const geometry>" */
+const char *smk_kernel_name(smk_ctx *ctx);
 
 /* ---- data ------------------------------------------------------------- */
 /* host (unpadded, pageable or pinned) -> device (padded); tallies are zeroed.
- * fine_flux may be NULL (initial scalar flux = 0). */
+ * fine_flux may be NULL (initial scalar flux = 0).  Returns when the host arrays may be reused. */
 int   smk_upload(smk_ctx *ctx, const float *fine_source, const float *fine_flux,
                  const float *sigT);
+/* same, enqueue only: the copies are ordered on the context's stream before any later smk_run*;
+ * the host arrays must stay unchanged until smk_synchronize (pinned memory makes the copies truly
+ * asynchronous; pageable memory is staged by the driver) */
+int   smk_upload_async(smk_ctx *ctx, const float *fine_source, const float *fine_flux,
+                       const float *sigT);
+/* rows [row_begin, row_begin + rows) of one array (a "row" is G floats: R*F rows for source and
+ * flux, R rows for sigT), enqueue only.  For callers that split the upload over ranks and complete
+ * the replicas with an all-gather on the device arrays (smk_device_*).  Tallies are NOT reset.
+ * After a partial sigT upload the library no longer knows max(sigT): call smk_scan_sigt_max once
+ * the device array is complete, or the POLY exponential stays in its (slower) wide-range form. */
+#define SMK_ARRAY_SOURCE 0
+#define SMK_ARRAY_FLUX   1
+#define SMK_ARRAY_SIGT   2
+int   smk_upload_rows_async(smk_ctx *ctx, int array, int64_t row_begin, int64_t rows, const float *host);
+/* max(sigT) of the device array (one small kernel + 4-byte read back; synchronises the stream) */
+int   smk_scan_sigt_max(smk_ctx *ctx, float *max_out);
 /* device-side deterministic fill, bit-identical to the host stream fill that
  * replaces init.c:64-75; sigt_floor = 0 for U[0,1) */
 int   smk_fill_device(smk_ctx *ctx, float sigt_floor);
@@ -111,9 +159,13 @@ int   smk_reset_tallies(smk_ctx *ctx);
 /* fine_flux_out[R][F][G] = initial flux + tallies accumulated since the last
  * reset (kernel.c:274-277 applied to every replayed segment) */
 int   smk_download_flux(smk_ctx *ctx, float *fine_flux_out);
-/* outgoing psi of tracks [track_begin, track_end) of the LAST run:
- * psi_out[(t - track_begin) * G + g]; needs SMK_FLAG_KEEP_PSI */
-int   smk_download_psi(smk_ctx *ctx, float *psi_out);
+/* rows [row_begin, row_begin + rows) of the same (out[rows][G]), enqueue only: for callers that
+ * reduce-scatter the tallies over ranks and read back one slice per rank */
+int   smk_download_flux_rows_async(smk_ctx *ctx, int64_t row_begin, int64_t rows, float *out);
+/* outgoing psi of the tracks [track_begin, track_end) swept by the LAST smk_run*:
+ * psi_out[(t - track_begin) * G + g]; n_tracks must equal track_end - track_begin of that run
+ * (SMK_EINVAL otherwise: it is the capacity of psi_out); needs SMK_FLAG_KEEP_PSI */
+int   smk_download_psi(smk_ctx *ctx, float *psi_out, int64_t n_tracks);
 /* sum over replayed segments s of (QSR_id*F + FAI_id + 1) * ((s & 0xFFFF) + 1)
  * mod 2^64, accumulated since the last reset: the indexing fingerprint */
 int   smk_download_checksum(smk_ctx *ctx, uint64_t *checksum);
@@ -170,7 +222,10 @@ typedef struct smk_multi smk_multi;
 int   smk_multi_create(const smk_params *p, int n_devices, const int *devices, int allreduce,
                        smk_multi **out);
 void  smk_multi_destroy(smk_multi *m);
+/* ONE host->device copy (to the first device), then every other device pulls the padded arrays over
+ * NVLink peer copies, all devices in parallel */
 int   smk_multi_upload(smk_multi *m, const float *fine_source, const float *fine_flux, const float *sigT);
+int   smk_multi_set_geometry(smk_multi *m, const smk_geometry *g);
 int   smk_multi_fill_device(smk_multi *m, float sigt_floor);
 /* sweep all tracks + all-reduce.  kernel_seconds = slowest device's kernel (CUDA events),
  * total_seconds = wall clock from first launch to the end of the all-reduce; either may be NULL */
@@ -182,11 +237,17 @@ int   smk_multi_device_count(const smk_multi *m);
 
 /* ---- diagnostics ------------------------------------------------------- */
 /* d_out[i] = exp(-tau[i]) as evaluated by exp_mode (host arrays, n elements);
- * used to sweep the exponential against libm */
+ * used to sweep the exponential against libm.  exp_mode | SMK_DEBUG_EXP_PACKED evaluates the
+ * packed (FP32x2) form of the FAST kernels; SMK_DEBUG_EXP_WIDE selects POLY's wide-range form */
+#define SMK_DEBUG_EXP_PACKED 0x100
+#define SMK_DEBUG_EXP_WIDE   0x200
 int   smk_debug_exp(int exp_mode, const float *tau, float *out, int64_t n, int device);
 /* (QSR_id, FAI_id) of segments [seg_begin, seg_begin+n) as the kernel draws them */
 int   smk_debug_segment_ids(const smk_params *p, int64_t seg_begin, int64_t n,
                             int32_t *qsr_out, int32_t *fai_out);
+/* dz, zin, weight, mu, mu2, ds of the same segments as the kernels derive them: geom6_out[n][6] */
+int   smk_debug_segment_geometry(const smk_params *p, const smk_geometry *g, int64_t seg_begin, int64_t n,
+                                 float *geom6_out);
 
 #ifdef __cplusplus
 }

@@ -32,6 +32,11 @@ EXP_POLY, EXP_MUFU, EXP_GLIBC, EXP_TABLE = 0, 1, 2, 3
 MATH_FAST, MATH_STRICT = 0, 1
 FLAG_KEEP_PSI = 1
 FLAG_TALLY_F64 = 2
+FLAG_SEGMENT_GEOMETRY = 4
+ARRAY_SOURCE, ARRAY_FLUX, ARRAY_SIGT = 0, 1, 2
+DEBUG_EXP_PACKED, DEBUG_EXP_WIDE = 0x100, 0x200
+# kernel.c:99-104: dz, zin, weight, mu, mu2, ds
+REFERENCE_GEOMETRY = (0.1, 0.3, 0.5, 0.9, 0.3, 0.7)
 
 EXP_MODES = {"poly": EXP_POLY, "mufu": EXP_MUFU, "glibc": EXP_GLIBC, "table": EXP_TABLE}
 MATH_MODES = {"fast": MATH_FAST, "strict": MATH_STRICT}
@@ -57,6 +62,12 @@ class Params(C.Structure):
     ]
 
 
+class Geometry(C.Structure):
+    """struct smk_geometry (include/smk.h): base values of kernel.c:99-104 + per-segment spread."""
+    _fields_ = [("dz", C.c_float), ("zin", C.c_float), ("weight", C.c_float), ("mu", C.c_float),
+                ("mu2", C.c_float), ("ds", C.c_float), ("spread", C.c_float)]
+
+
 def build(verbose: bool = False) -> str:
     """Compile lib/libsmk.so and bin/SimpleMOC-kernel for sm_100a (nvcc cross-compiles without a GPU)."""
     cmd = ["make", "-C", HERE, "all"] + ([] if verbose else ["-s"])
@@ -78,7 +89,10 @@ ABI_SYMBOLS = (
     "smk_alloc_host", "smk_free_host", "smk_debug_exp", "smk_debug_segment_ids",
     "smk_multi_create", "smk_multi_destroy", "smk_multi_upload", "smk_multi_fill_device",
     "smk_multi_run", "smk_multi_download_flux", "smk_multi_download_checksum",
-    "smk_multi_device_count",
+    "smk_multi_device_count", "smk_multi_set_geometry",
+    "smk_set_geometry", "smk_get_geometry", "smk_kernel_name", "smk_upload_async",
+    "smk_upload_rows_async", "smk_scan_sigt_max", "smk_download_flux_rows_async",
+    "smk_debug_segment_geometry",
 )
 
 
@@ -102,10 +116,21 @@ def _load() -> C.CDLL:
     L.smk_destroy.restype = None
     L.smk_set_stream.argtypes = [vp, vp]
     L.smk_upload.argtypes = [vp, vp, vp, vp]
+    L.smk_device_sigT.argtypes = [vp]
     L.smk_fill_device.argtypes = [vp, C.c_float]
     L.smk_reset_tallies.argtypes = [vp]
     L.smk_download_flux.argtypes = [vp, vp]
-    L.smk_download_psi.argtypes = [vp, vp]
+    L.smk_download_psi.argtypes = [vp, vp, i64]
+    L.smk_set_geometry.argtypes = [vp, C.POINTER(Geometry)]
+    L.smk_get_geometry.argtypes = [vp, C.POINTER(Geometry)]
+    L.smk_kernel_name.argtypes = [vp]
+    L.smk_kernel_name.restype = C.c_char_p
+    L.smk_upload_async.argtypes = [vp, vp, vp, vp]
+    L.smk_upload_rows_async.argtypes = [vp, i32, i64, i64, vp]
+    L.smk_scan_sigt_max.argtypes = [vp, C.POINTER(C.c_float)]
+    L.smk_download_flux_rows_async.argtypes = [vp, i64, i64, vp]
+    L.smk_multi_set_geometry.argtypes = [vp, C.POINTER(Geometry)]
+    L.smk_debug_segment_geometry.argtypes = [C.POINTER(Params), C.POINTER(Geometry), i64, i64, _f32p]
     L.smk_download_checksum.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.smk_run.argtypes = [vp, i64, i64, C.POINTER(C.c_double)]
     L.smk_run_async.argtypes = [vp, i64, i64]
@@ -164,6 +189,10 @@ class Input:
     math_mode: str = "fast"
     device: int = 0
     tally_f64: bool = False              # diagnostic: f64 tally accumulators (SMK_FLAG_TALLY_F64)
+    # per-segment geometry (SMK_FLAG_SEGMENT_GEOMETRY): kernel.c:99-104 as base values + spread
+    segment_geometry: bool = False
+    geometry: tuple = REFERENCE_GEOMETRY
+    geometry_spread: float = 0.25
 
     def finalize(self) -> "Input":
         """main.c:18-19: source_3D_regions = ceil(2D * coarse / decomp)."""
@@ -180,6 +209,8 @@ class Input:
             self.finalize()
         if self.tally_f64:
             flags |= FLAG_TALLY_F64
+        if self.segment_geometry:
+            flags |= FLAG_SEGMENT_GEOMETRY
         return Params(self.source_3D_regions, self.fine_axial_intervals, self.egroups,
                       self.seg_per_thread, self.segments, self.seed, EXP_MODES[self.exp_mode],
                       MATH_MODES[self.math_mode], self.device, flags)
@@ -201,11 +232,21 @@ class Context:
         self.R, self.F, self.G = self.p.source_3D_regions, self.p.fine_axial_intervals, self.p.egroups
         self.G_pad = lib.smk_padded_groups(self.G)
         self.n_tracks = lib.smk_num_tracks(self.p.segments, self.p.seg_per_track)
+        if I.segment_geometry:
+            self.set_geometry(I.geometry, I.geometry_spread)
 
     def close(self):
         if self._h:
             lib.smk_destroy(self._h)
             self._h = C.c_void_p()
+
+    def set_geometry(self, base=REFERENCE_GEOMETRY, spread: float = 0.25):
+        g = Geometry(*base, spread)
+        _check(lib.smk_set_geometry(self._h, C.byref(g)))
+
+    @property
+    def kernel_name(self) -> str:
+        return lib.smk_kernel_name(self._h).decode()
 
     def __enter__(self):
         return self
@@ -233,6 +274,22 @@ class Context:
 
     def upload(self, fine_source, fine_flux, sigT):
         _check(lib.smk_upload(self._h, self._ptr(fine_source), self._ptr(fine_flux), self._ptr(sigT)))
+
+    def upload_async(self, fine_source, fine_flux, sigT):
+        """Enqueue only; the host arrays must stay unchanged until synchronize()."""
+        _check(lib.smk_upload_async(self._h, self._ptr(fine_source), self._ptr(fine_flux), self._ptr(sigT)))
+
+    def upload_rows_async(self, array: int, row_begin: int, rows: int, host):
+        """rows [row_begin, row_begin+rows) of ARRAY_SOURCE / ARRAY_FLUX (R*F rows) or ARRAY_SIGT (R rows)."""
+        _check(lib.smk_upload_rows_async(self._h, array, row_begin, rows, self._ptr(host)))
+
+    def scan_sigt_max(self) -> float:
+        v = C.c_float(0.0)
+        _check(lib.smk_scan_sigt_max(self._h, C.byref(v)))
+        return v.value
+
+    def download_flux_rows_async(self, row_begin: int, rows: int, out):
+        _check(lib.smk_download_flux_rows_async(self._h, row_begin, rows, self._ptr(out)))
 
     def fill_device(self, sigt_floor: float = 0.0):
         _check(lib.smk_fill_device(self._h, sigt_floor))
@@ -265,7 +322,7 @@ class Context:
 
     def download_psi(self, n_tracks: int):
         out = np.empty((n_tracks, self.G), np.float32)
-        _check(lib.smk_download_psi(self._h, out.ctypes.data))
+        _check(lib.smk_download_psi(self._h, out.ctypes.data, n_tracks))
         return out
 
     def checksum(self) -> int:
@@ -286,6 +343,14 @@ class Context:
     def padded_elems(self) -> int:
         return lib.smk_padded_elems(self._h)
 
+    @property
+    def source_ptr(self) -> int:
+        return lib.smk_device_source(self._h)
+
+    @property
+    def sigt_ptr(self) -> int:
+        return lib.smk_device_sigT(self._h)
+
 
 class MultiContext:
     """One process, several GPUs: tracks sharded by range, one all-reduce of the tally deltas
@@ -299,6 +364,9 @@ class MultiContext:
         _check(lib.smk_multi_create(C.byref(self.p), n_devices, ids, {"peer": 0, "nccl": 1}[allreduce],
                                     C.byref(self._h)))
         self.R, self.F, self.G = self.p.source_3D_regions, self.p.fine_axial_intervals, self.p.egroups
+        if I.segment_geometry:
+            g = Geometry(*I.geometry, I.geometry_spread)
+            _check(lib.smk_multi_set_geometry(self._h, C.byref(g)))
 
     def close(self):
         if self._h:
@@ -344,10 +412,22 @@ def run_kernel(I: Input, fine_source: np.ndarray, fine_flux: np.ndarray, sigT: n
     return ks.value, ts.value
 
 
-def debug_exp(exp_mode: str, tau: np.ndarray, device: int = 0) -> np.ndarray:
+def debug_exp(exp_mode: str, tau: np.ndarray, device: int = 0, packed: bool = False, wide: bool = False) -> np.ndarray:
+    """exp(-tau) as the kernels evaluate it; packed = the FP32x2 form of the FAST kernels,
+    wide = POLY's wide-range form (MUFU.EX2 beyond tau = 0.7)."""
     tau = np.ascontiguousarray(tau, np.float32)
     out = np.empty_like(tau)
-    _check(lib.smk_debug_exp(EXP_MODES[exp_mode], tau, out, tau.size, device))
+    mode = EXP_MODES[exp_mode] | (DEBUG_EXP_PACKED if packed else 0) | (DEBUG_EXP_WIDE if wide else 0)
+    _check(lib.smk_debug_exp(mode, tau, out, tau.size, device))
+    return out
+
+
+def debug_segment_geometry(I: Input, seg_begin: int, n: int) -> np.ndarray:
+    """(n, 6) dz, zin, weight, mu, mu2, ds of segments [seg_begin, seg_begin+n) as the kernels derive them."""
+    p = I.params()
+    g = Geometry(*I.geometry, I.geometry_spread)
+    out = np.empty((n, 6), np.float32)
+    _check(lib.smk_debug_segment_geometry(C.byref(p), C.byref(g), seg_begin, n, out))
     return out
 
 

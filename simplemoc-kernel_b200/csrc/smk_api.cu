@@ -70,43 +70,50 @@ static void build_exp_table(ExpTable &t)
 struct Shape {
     int groups_pad;   // floats per padded row
     int lpt;          // lanes per track
-    int nchunk;       // float4 per lane per row
+    int nchunk;       // float4 per lane per group block
+    int group_blocks; // blocks of 4*lpt*nchunk groups per row (> 1 only for more than 256 groups)
 };
 
+// G <= 128: one float4 per lane, LPT = next power of two of ceil(G/4) lanes per track.
+// G > 128: blocks of 256 groups (two float4 per lane, the fastest measured shape), as many as the row needs.
 static bool shape_for(int groups, Shape &s)
 {
     if (groups < 1) return false;
-    int f4 = (groups + 3) / 4;
+    const int f4 = (groups + 3) / 4;
     if (f4 <= 32) {
         int l = 1;
         while (l < f4) l <<= 1;
         s.lpt = l;
         s.nchunk = 1;
+        s.group_blocks = 1;
     } else {
-        int c = (f4 + 31) / 32;
-        int n = 2;
-        while (n < c) n <<= 1;
-        if (n > 8) return false;
         s.lpt = 32;
-        s.nchunk = n;
+        s.nchunk = 2;
+        s.group_blocks = (f4 + 63) / 64;
     }
-    s.groups_pad = 4 * s.lpt * s.nchunk;
+    s.groups_pad = 4 * s.lpt * s.nchunk * s.group_blocks;
     return true;
 }
 
 typedef void (*AttenuateFn)(const KernelArgs);
 
+struct KernelChoice {
+    AttenuateFn fn;
+    const char *family;
+};
 
-template <int LPT, int NCHUNK>
-static AttenuateFn pick_modes(int math, int expm)
+// general kernel: every shape x arithmetic x exponential x geometry
+template <int LPT, int NCHUNK, bool GEOM>
+static AttenuateFn pick_general_modes(int math, int expm)
 {
 #define SMK_PICK(M, E) \
-    if (math == M && expm == E) return attenuate_tracks<LPT, NCHUNK, M, E>;
+    if (math == M && expm == E) return attenuate_tracks<LPT, NCHUNK, M, E, GEOM>;
     SMK_PICK(kMathFast, kExpPoly)
+    SMK_PICK(kMathFast, kExpPolyWide)
     SMK_PICK(kMathFast, kExpMufu)
     SMK_PICK(kMathFast, kExpGlibc)
     SMK_PICK(kMathFast, kExpTable)
-    SMK_PICK(kMathStrict, kExpPoly)
+    SMK_PICK(kMathStrict, kExpPoly)      // the scalar polynomial is range-safe by itself
     SMK_PICK(kMathStrict, kExpMufu)
     SMK_PICK(kMathStrict, kExpGlibc)
     SMK_PICK(kMathStrict, kExpTable)
@@ -114,98 +121,70 @@ static AttenuateFn pick_modes(int math, int expm)
     return nullptr;
 }
 
-static AttenuateFn pick_kernel(const Shape &s, int math, int expm)
+template <bool GEOM>
+static AttenuateFn pick_general(const Shape &s, int math, int expm)
 {
+    if (math == kMathStrict && expm == kExpPolyWide) expm = kExpPoly;
     if (s.nchunk == 1) {
         switch (s.lpt) {
-            case 1: return pick_modes<1, 1>(math, expm);
-            case 2: return pick_modes<2, 1>(math, expm);
-            case 4: return pick_modes<4, 1>(math, expm);
-            case 8: return pick_modes<8, 1>(math, expm);
-            case 16: return pick_modes<16, 1>(math, expm);
-            case 32: return pick_modes<32, 1>(math, expm);
+            case 1: return pick_general_modes<1, 1, GEOM>(math, expm);
+            case 2: return pick_general_modes<2, 1, GEOM>(math, expm);
+            case 4: return pick_general_modes<4, 1, GEOM>(math, expm);
+            case 8: return pick_general_modes<8, 1, GEOM>(math, expm);
+            case 16: return pick_general_modes<16, 1, GEOM>(math, expm);
+            case 32: return pick_general_modes<32, 1, GEOM>(math, expm);
         }
-    } else if (s.lpt == 32) {
-        switch (s.nchunk) {
-            case 2: return pick_modes<32, 2>(math, expm);
-            case 4: return pick_modes<32, 4>(math, expm);
-            case 8: return pick_modes<32, 8>(math, expm);
-        }
+    } else if (s.lpt == 32 && s.nchunk == 2) {
+        return pick_general_modes<32, 2, GEOM>(math, expm);
     }
     return nullptr;
 }
 
-// TMA-staged variants exist for the one-track-per-warp shapes (LPT = 32), FAST math only.
-template <int NCHUNK, int STAGES>
-static AttenuateFn pick_staged_exp(int expm)
+// one track per warp, FAST arithmetic: 4 groups per lane (65..128 groups) or 2 (33..64)
+template <int GPL, bool F64, bool GEOM>
+static AttenuateFn pick_warp_track_exp(int expm)
 {
     switch (expm) {
-        case kExpPoly: return attenuate_tracks_staged<NCHUNK, kExpPoly, STAGES>;
-        case kExpMufu: return attenuate_tracks_staged<NCHUNK, kExpMufu, STAGES>;
-        case kExpGlibc: return attenuate_tracks_staged<NCHUNK, kExpGlibc, STAGES>;
-        case kExpTable: return attenuate_tracks_staged<NCHUNK, kExpTable, STAGES>;
+        case kExpPoly: return attenuate_warp_track<GPL, kExpPoly, F64, GEOM>;
+        case kExpPolyWide: return attenuate_warp_track<GPL, kExpPolyWide, F64, GEOM>;
+        case kExpMufu: return attenuate_warp_track<GPL, kExpMufu, F64, GEOM>;
+        case kExpGlibc: return attenuate_warp_track<GPL, kExpGlibc, F64, GEOM>;
+        case kExpTable: return attenuate_warp_track<GPL, kExpTable, F64, GEOM>;
     }
     return nullptr;
 }
 
-template <int NCHUNK, bool PREFETCH, bool DEFER = false, bool L1PF = false>
-static AttenuateFn pick_pf_exp(int expm)
+template <int GPL>
+static AttenuateFn pick_warp_track(int expm, bool f64, bool geom)
 {
-    switch (expm) {
-        case kExpPoly: return attenuate_tracks_pf<NCHUNK, kExpPoly, PREFETCH, DEFER, L1PF>;
-        case kExpMufu: return attenuate_tracks_pf<NCHUNK, kExpMufu, PREFETCH, DEFER, L1PF>;
-        case kExpGlibc: return attenuate_tracks_pf<NCHUNK, kExpGlibc, PREFETCH, DEFER, L1PF>;
-        case kExpTable: return attenuate_tracks_pf<NCHUNK, kExpTable, PREFETCH, DEFER, L1PF>;
-    }
-    return nullptr;
+    if (f64) return geom ? pick_warp_track_exp<GPL, true, true>(expm) : pick_warp_track_exp<GPL, true, false>(expm);
+    return geom ? pick_warp_track_exp<GPL, false, true>(expm) : pick_warp_track_exp<GPL, false, false>(expm);
 }
 
-// flat-loop kernels for the one-track-per-warp shapes, FAST math: "flat" (loads at use) and
-// "prefetch" (software-pipelined through a second register set)
-static AttenuateFn pick_half(int expm)
+// expm is the internal mode (kExpPolyWide resolved by the caller)
+static KernelChoice choose_kernel(const Shape &s, int math, int expm, bool f64, bool geom)
 {
-    switch (expm) {
-        case kExpPoly: return attenuate_tracks_half<kExpPoly>;
-        case kExpMufu: return attenuate_tracks_half<kExpMufu>;
-        case kExpGlibc: return attenuate_tracks_half<kExpGlibc>;
-        case kExpTable: return attenuate_tracks_half<kExpTable>;
-    }
-    return nullptr;
-}
-
-static AttenuateFn pick_flat(const Shape &s, int math, int expm, bool prefetch, bool defer = false, bool l1pf = false)
-{
-    // 33..64 groups (G_pad = 64): one track per warp with two groups per lane
-    if (math == kMathFast && s.lpt == 16 && s.nchunk == 1 && !prefetch && !defer && !l1pf) return pick_half(expm);
-    if (math != kMathFast || s.lpt != 32) return nullptr;
-    if (l1pf) return s.nchunk == 1 ? pick_pf_exp<1, false, false, true>(expm) : nullptr;
-    if (defer) return s.nchunk == 1 ? pick_pf_exp<1, false, true>(expm) : nullptr;
-    if (prefetch) return s.nchunk == 1 ? pick_pf_exp<1, true>(expm) : nullptr;
-    switch (s.nchunk) {
-        case 1: return pick_pf_exp<1, false>(expm);
-    }
-    return nullptr;
-}
-
-static AttenuateFn pick_staged(const Shape &s, int math, int expm, int stages)
-{
-    if (math != kMathFast || s.lpt != 32 || s.nchunk != 1) return nullptr;
-    switch (stages) {
-        case 2: return pick_staged_exp<1, 2>(expm);
-        case 3: return pick_staged_exp<1, 3>(expm);
-    }
-    return nullptr;
+    if (math == kMathFast && s.nchunk == 1 && s.lpt == 32) return {pick_warp_track<4>(expm, f64, geom), "attenuate_warp_track<4 groups/lane"};
+    if (math == kMathFast && s.nchunk == 1 && s.lpt == 16) return {pick_warp_track<2>(expm, f64, geom), "attenuate_warp_track<2 groups/lane"};
+    return {geom ? pick_general<true>(s, math, expm) : pick_general<false>(s, math, expm), "attenuate_tracks<general"};
 }
 
 }  // namespace smk
+
+#ifdef SMK_TUNING
+#include "smk_kernels_tuning.cuh"
+#endif
 
 using namespace smk;
 
 struct smk_ctx {
     smk_params p;
     Shape shape;
-    AttenuateFn kernel;
-    int stages;              // > 0: TMA-staged kernel with this many ring slots per warp
+    smk_geometry geom;       // base + spread (reference constants unless SMK_FLAG_SEGMENT_GEOMETRY)
+    AttenuateFn kernel;      // instantiation of the last selection
+    AttenuateFn tuning_kernel;  // -DSMK_TUNING builds: SMK_KERNEL=<variant> override (nullptr otherwise)
+    int exp_internal;        // kExp* of `kernel`
+    char kernel_name[160];
     size_t dyn_smem;
     int sm_count;
     int blocks_per_sm;
@@ -219,13 +198,42 @@ struct smk_ctx {
     int64_t last_begin, last_end;
     unsigned long long *d_checksum;
     unsigned long long *d_work;  // dynamic track scheduling counter
+    unsigned int *d_max_bits;    // smk_scan_sigt_max scratch
     double *d_tally64;           // SMK_FLAG_TALLY_F64: f64 tally accumulators, [R][F][G_pad]
+    float sigt_max;              // max(sigT) of the device data, +inf when unknown (partial uploads)
     cudaStream_t stream;
     bool own_stream;
     cudaEvent_t ev0, ev1;
     bool have_data;
     int64_t launches;
 };
+
+#ifdef SMK_TUNING
+// SMK_KERNEL=<variant>: measured alternatives for the 65..128-group FAST shape (smk_kernels_tuning.cuh)
+static int smk_tuning_select(smk_ctx *c)
+{
+    const char *variant = getenv("SMK_KERNEL");
+    if (!variant || !*variant || strcmp(variant, "default") == 0) return SMK_OK;
+    const bool shape_ok = c->shape.lpt == 32 && c->shape.nchunk == 1 && c->p.math_mode == kMathFast &&
+                          !(c->p.flags & (SMK_FLAG_TALLY_F64 | SMK_FLAG_SEGMENT_GEOMETRY)) &&
+                          (c->p.exp_mode == kExpPoly || c->p.exp_mode == kExpMufu);
+    if (!shape_ok) return SMK_OK;     // variants exist for that shape only; everything else runs the product kernel
+    AttenuateFn fn = nullptr;
+    if (strcmp(variant, "oldflat") == 0) fn = pick_pf_exp<false, false, false>(c->p.exp_mode);
+    else if (strcmp(variant, "prefetch") == 0) fn = pick_pf_exp<true, false, false>(c->p.exp_mode);
+    else if (strcmp(variant, "defer") == 0) fn = pick_pf_exp<false, true, false>(c->p.exp_mode);
+    else if (strcmp(variant, "l1pf") == 0) fn = pick_pf_exp<false, false, true>(c->p.exp_mode);
+    else if (strcmp(variant, "staged2") == 0 || strcmp(variant, "staged3") == 0) {
+        const int stages = variant[6] - '0';
+        fn = stages == 2 ? pick_staged_exp<1, 2>(c->p.exp_mode) : pick_staged_exp<1, 3>(c->p.exp_mode);
+        c->dyn_smem = (size_t)(kThreadsPerBlock / 32) * stages * 4 * c->shape.groups_pad * sizeof(float);
+    } else {
+        return fail(SMK_EINVAL, "unknown SMK_KERNEL variant '%s'", variant);
+    }
+    c->tuning_kernel = fn;
+    return SMK_OK;
+}
+#endif
 
 static int validate(const smk_params *p, Shape &shape)
 {
@@ -240,10 +248,59 @@ static int validate(const smk_params *p, Shape &shape)
         return fail(SMK_EINVAL, "unknown exp_mode %d", p->exp_mode);
     if (p->math_mode != SMK_MATH_FAST && p->math_mode != SMK_MATH_STRICT)
         return fail(SMK_EINVAL, "unknown math_mode %d", p->math_mode);
-    if (!shape_for(p->egroups, shape))
-        return fail(SMK_EINVAL, "egroups = %d unsupported (max 1024)", p->egroups);
+    if (p->flags & ~(SMK_FLAG_KEEP_PSI | SMK_FLAG_TALLY_F64 | SMK_FLAG_SEGMENT_GEOMETRY))
+        return fail(SMK_EINVAL, "unknown flag bits %#x", p->flags);
+    if (!shape_for(p->egroups, shape)) return fail(SMK_EINVAL, "egroups = %d unsupported", p->egroups);
     if ((int64_t)p->source_3D_regions * p->fine_axial_intervals * (shape.groups_pad / 4) >= (1ll << 31))
         return fail(SMK_EINVAL, "regions * intervals * padded groups / 4 must be < 2^31 (32-bit row offsets)");
+    return SMK_OK;
+}
+
+static const smk_geometry kReferenceGeometry = {Geometry::dz, Geometry::zin, Geometry::weight, Geometry::mu,
+                                                Geometry::mu2, Geometry::ds, 0.0f};
+
+static int check_geometry(const smk_geometry *g)
+{
+    if (!g) return fail(SMK_EINVAL, "geometry is NULL");
+    if (!(g->dz > 0.0f) || !(g->ds > 0.0f) || !(g->spread >= 0.0f && g->spread < 1.0f) || !std::isfinite(g->dz) ||
+        !std::isfinite(g->zin) || !std::isfinite(g->weight) || !std::isfinite(g->mu) || !std::isfinite(g->mu2) ||
+        !std::isfinite(g->ds))
+        return fail(SMK_EINVAL, "geometry needs finite values, dz > 0, ds > 0 and 0 <= spread < 1");
+    return SMK_OK;
+}
+
+// Resolve the kernel instantiation for the context's current state (exp form depends on the data's
+// max(sigT) and on the geometry's largest ds) and its occupancy.
+static int select_kernel(smk_ctx *c)
+{
+    const bool geom = (c->p.flags & SMK_FLAG_SEGMENT_GEOMETRY) != 0;
+    const bool f64 = (c->p.flags & SMK_FLAG_TALLY_F64) != 0;
+    int expm = c->p.exp_mode;
+    const char *exp_name[] = {"poly", "mufu", "glibc", "table", "poly+mufu beyond tau 0.7"};
+    if (expm == kExpPoly) {
+        const float ds_max = geom ? c->geom.ds * (1.0f + c->geom.spread) : c->geom.ds;
+        // tau = sigT * ds <= bound; `!(<=)` also catches an unknown (+inf) or NaN bound
+        if (!(c->sigt_max * ds_max <= kPolyMaxTau)) expm = kExpPolyWide;
+    }
+    AttenuateFn fn = c->tuning_kernel;
+    const char *family = "tuning variant";
+    if (!fn) {
+        const KernelChoice k = choose_kernel(c->shape, c->p.math_mode, expm, f64, geom);
+        fn = k.fn;
+        family = k.family;
+    }
+    if (!fn) return fail(SMK_EINVAL, "no kernel for egroups=%d math=%d exp=%d", c->p.egroups, c->p.math_mode, expm);
+    if (fn != c->kernel) {
+        c->kernel = fn;
+        if (c->dyn_smem > 0)
+            SMK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dyn_smem));
+        SMK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->blocks_per_sm, fn, kThreadsPerBlock, c->dyn_smem));
+        if (c->blocks_per_sm < 1) c->blocks_per_sm = 1;
+    }
+    c->exp_internal = expm;
+    snprintf(c->kernel_name, sizeof c->kernel_name, "%s, %s, %s, %s tally, %s geometry>", family,
+             c->p.math_mode == kMathStrict ? "strict" : "fast", exp_name[expm], f64 ? "f64" : "f32",
+             geom ? "per-segment" : "const");
     return SMK_OK;
 }
 
@@ -302,73 +359,36 @@ int smk_create(const smk_params *p, smk_ctx **out)
     memset(c, 0, sizeof(*c));
     c->p = *p;
     c->shape = shape;
-    c->kernel = pick_kernel(shape, p->math_mode, p->exp_mode);
-    // Kernel variants.  Default: the flat-loop kernel where it exists (one track per warp, FAST
-    // math), else the general kernel.  SMK_KERNEL = direct | flat | l1pf | defer | prefetch | staged2 |
-    // staged3 selects another variant for the tuning experiments recorded in DESIGN.md section 5.3.
-    const char *variant = getenv("SMK_KERNEL");
-    if (!variant || !*variant) variant = "flat";
-    if (strcmp(variant, "flat") == 0 || strcmp(variant, "prefetch") == 0 || strcmp(variant, "defer") == 0 ||
-        strcmp(variant, "l1pf") == 0) {
-        AttenuateFn pf = pick_flat(shape, p->math_mode, p->exp_mode, strcmp(variant, "prefetch") == 0,
-                                   strcmp(variant, "defer") == 0, strcmp(variant, "l1pf") == 0);
-        if (pf) c->kernel = pf;
-    } else if (strncmp(variant, "staged", 6) == 0) {
-        const int stages = atoi(variant + 6);
-        AttenuateFn staged = pick_staged(shape, p->math_mode, p->exp_mode, stages);
-        if (staged) {
-            c->kernel = staged;
-            c->stages = stages;
-            c->dyn_smem = (size_t)(kThreadsPerBlock / 32) * stages * 4 * shape.groups_pad * sizeof(float);
-        }
-    } else if (strcmp(variant, "direct") != 0) {
-        delete c;
-        return fail(SMK_EINVAL, "unknown SMK_KERNEL variant '%s'", variant);
-    }
-    if (!c->kernel) {
-        delete c;
-        return fail(SMK_EINVAL, "no kernel for egroups=%d math=%d exp=%d", p->egroups, p->math_mode,
-                    p->exp_mode);
-    }
-    if (p->flags & SMK_FLAG_TALLY_F64) {
-        // the f64 accumulators are only wired into the flat one-track-per-warp kernel
-        if (shape.lpt != 32 || c->kernel != pick_flat(shape, p->math_mode, p->exp_mode, false)) {
-            delete c;
-            return fail(SMK_EINVAL, "SMK_FLAG_TALLY_F64 needs 65..128 groups, FAST math and the default kernel");
-        }
-    }
+    c->geom = kReferenceGeometry;
+    if (p->flags & SMK_FLAG_SEGMENT_GEOMETRY) c->geom.spread = 0.25f;
+    c->sigt_max = INFINITY;           // nothing uploaded yet
     c->rows = (int64_t)p->source_3D_regions * p->fine_axial_intervals;
     // few tally rows => L2 atomics on the same addresses serialise: spread them over replicas so that
     // at least ~4096 rows are in play (1 for the reference's default 33750 rows)
     c->replicas = 1;
-    if (c->rows < 4096) {
+    if (c->rows < 4096 && !(p->flags & SMK_FLAG_TALLY_F64)) {
         c->replicas = (int)((4096 + c->rows - 1) / c->rows);
         if (c->replicas > 32) c->replicas = 32;
     }
-    if (const char *r = getenv("SMK_TALLY_REPLICAS")) {       // tuning knob, like SMK_KERNEL
-        const int v = atoi(r);
-        if (v >= 1 && v <= 256) c->replicas = v;
-    }
     c->n_tracks = smk_num_tracks(p->segments, p->seg_per_track);
 
+    // every failure from here on goes through the single cleanup path (smk_destroy)
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) { c->own_stream = true; e = cudaEventCreate(&c->ev0); }
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     cudaDeviceProp prop;
-    SMK_CUDA(cudaGetDeviceProperties(&prop, p->device));
-    c->sm_count = prop.multiProcessorCount;
-    if (c->dyn_smem > 0)
-        SMK_CUDA(cudaFuncSetAttribute(c->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dyn_smem));
-    SMK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->blocks_per_sm, c->kernel,
-                                                           kThreadsPerBlock, c->dyn_smem));
-    if (c->blocks_per_sm < 1) c->blocks_per_sm = 1;
-
-    ExpTable tab;
-    build_exp_table(tab);
-    SMK_CUDA(cudaMemcpyToSymbol(c_exp_table, &tab, sizeof(tab)));
-    SMK_CUDA(cudaMemcpyToSymbol(c_exp2f_tab, h_exp2f_tab, sizeof(h_exp2f_tab)));
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, p->device);
+    if (e == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    if (e == cudaSuccess) {
+        ExpTable tab;
+        build_exp_table(tab);
+        e = cudaMemcpyToSymbol(c_exp_table, &tab, sizeof(tab));
+    }
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_exp2f_tab, h_exp2f_tab, sizeof(h_exp2f_tab));
 
     const size_t slab = (size_t)c->rows * shape.groups_pad * sizeof(float);
     const size_t sig = (size_t)p->source_3D_regions * shape.groups_pad * sizeof(float);
     const size_t stage = (size_t)c->rows * p->egroups * sizeof(float);
-    cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(&c->d_source, slab);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_flux0, slab);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_tally, slab * c->replicas);
@@ -376,13 +396,11 @@ int smk_create(const smk_params *p, smk_ctx **out)
     if (e == cudaSuccess) e = cudaMalloc(&c->d_stage, stage);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_checksum, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_work, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_max_bits, sizeof(unsigned int));
     if (e == cudaSuccess && (p->flags & SMK_FLAG_TALLY_F64)) {
         e = cudaMalloc(&c->d_tally64, 2 * slab);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tally64, 0, 2 * slab, c->stream);
     }
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) { c->own_stream = true; e = cudaEventCreate(&c->ev0); }
-    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tally, 0, slab * c->replicas, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_flux0, 0, slab, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_checksum, 0, sizeof(unsigned long long), c->stream);
@@ -390,9 +408,20 @@ int smk_create(const smk_params *p, smk_ctx **out)
     if (e != cudaSuccess) {
         int code = (e == cudaErrorMemoryAllocation) ? SMK_ENOMEM : SMK_ECUDA;
         fail(code, "smk_create: %s", cudaGetErrorString(e));
+        cudaGetLastError();
         smk_destroy(c);
         return code;
     }
+#ifdef SMK_TUNING
+    rc = smk_tuning_select(c);        // SMK_KERNEL=<variant>; tuning builds only
+    if (rc != SMK_OK) { smk_destroy(c); return rc; }
+#endif
+    if (const char *r = getenv("SMK_TALLY_REPLICAS")) {       // tuning knob
+        const int v = atoi(r);
+        if (v >= 1 && v <= c->replicas) c->replicas = v;
+    }
+    rc = select_kernel(c);
+    if (rc != SMK_OK) { smk_destroy(c); return rc; }
     *out = c;
     return SMK_OK;
 }
@@ -409,6 +438,7 @@ void smk_destroy(smk_ctx *c)
     cudaFree(c->d_psi);
     cudaFree(c->d_checksum);
     cudaFree(c->d_work);
+    cudaFree(c->d_max_bits);
     cudaFree(c->d_tally64);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -427,25 +457,64 @@ int smk_set_stream(smk_ctx *c, void *cuda_stream)
     return SMK_OK;
 }
 
+int smk_set_geometry(smk_ctx *c, const smk_geometry *g)
+{
+    if (!c) return fail(SMK_EINVAL, "ctx is NULL");
+    if (!(c->p.flags & SMK_FLAG_SEGMENT_GEOMETRY))
+        return fail(SMK_ESTATE, "context created without SMK_FLAG_SEGMENT_GEOMETRY: the geometry is kernel.c:99-104");
+    int rc = check_geometry(g);
+    if (rc != SMK_OK) return rc;
+    c->geom = *g;
+    return select_kernel(c);
+}
+
+int smk_get_geometry(const smk_ctx *c, smk_geometry *g)
+{
+    if (!c || !g) return fail(SMK_EINVAL, "NULL argument");
+    *g = c->geom;
+    return SMK_OK;
+}
+
+const char *smk_kernel_name(smk_ctx *c)
+{
+    if (!c || select_kernel(c) != SMK_OK) return "";
+    return c->kernel_name;
+}
+
 static int layout_grid(int64_t n)
 {
     int64_t b = (n + 255) / 256;
     return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
 }
 
-// host unpadded -> device padded, through the unpadded staging buffer when G != G_pad
-static int upload_rows(smk_ctx *c, const float *h, float *d, int64_t rows, float pad)
+// host unpadded rows -> device padded rows [row_begin, row_begin + rows), through the unpadded
+// staging buffer when G != G_pad; enqueue only
+static int upload_rows(smk_ctx *c, const float *h, float *d, int64_t row_begin, int64_t rows, float pad)
 {
     const int G = c->p.egroups, Gp = c->shape.groups_pad;
+    if (rows <= 0) return SMK_OK;
     if (G == Gp) {
-        SMK_CUDA(cudaMemcpyAsync(d, h, (size_t)rows * G * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        SMK_CUDA(cudaMemcpyAsync(d + row_begin * Gp, h, (size_t)rows * G * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     } else {
-        SMK_CUDA(cudaMemcpyAsync(c->d_stage, h, (size_t)rows * G * sizeof(float), cudaMemcpyHostToDevice,
-                                 c->stream));
-        pad_rows<<<layout_grid(rows * Gp), 256, 0, c->stream>>>(c->d_stage, d, rows, G, Gp, pad);
+        SMK_CUDA(cudaMemcpyAsync(c->d_stage, h, (size_t)rows * G * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        pad_rows<<<layout_grid(rows * Gp), 256, 0, c->stream>>>(c->d_stage, d + row_begin * Gp, rows, G, Gp, pad);
         SMK_CUDA(cudaGetLastError());
+        c->launches += 1;
     }
     return SMK_OK;
+}
+
+// max of a host array; NaN or negative values make the bound unknown (+inf)
+static float host_max(const float *h, int64_t n)
+{
+    float m = 0.0f;
+    bool bad = false;
+    for (int64_t i = 0; i < n; ++i) {
+        const float v = h[i];
+        bad |= !(v >= 0.0f);
+        m = v > m ? v : m;
+    }
+    return bad ? INFINITY : m;
 }
 
 int smk_reset_tallies(smk_ctx *c)
@@ -460,22 +529,68 @@ int smk_reset_tallies(smk_ctx *c)
     return SMK_OK;
 }
 
-int smk_upload(smk_ctx *c, const float *fine_source, const float *fine_flux, const float *sigT)
+int smk_upload_async(smk_ctx *c, const float *fine_source, const float *fine_flux, const float *sigT)
 {
     if (!c) return fail(SMK_EINVAL, "ctx is NULL");
     if (!fine_source || !sigT) return fail(SMK_EINVAL, "fine_source and sigT are required");
     SMK_CUDA(cudaSetDevice(c->p.device));
     int rc;
-    if ((rc = upload_rows(c, fine_source, c->d_source, c->rows, 0.0f)) != SMK_OK) return rc;
-    if ((rc = upload_rows(c, sigT, c->d_sigT, c->p.source_3D_regions, 1.0f)) != SMK_OK) return rc;
+    if ((rc = upload_rows(c, fine_source, c->d_source, 0, c->rows, 0.0f)) != SMK_OK) return rc;
+    if ((rc = upload_rows(c, sigT, c->d_sigT, 0, c->p.source_3D_regions, 1.0f)) != SMK_OK) return rc;
     if (fine_flux) {
-        if ((rc = upload_rows(c, fine_flux, c->d_flux0, c->rows, 0.0f)) != SMK_OK) return rc;
+        if ((rc = upload_rows(c, fine_flux, c->d_flux0, 0, c->rows, 0.0f)) != SMK_OK) return rc;
     } else {
         SMK_CUDA(cudaMemsetAsync(c->d_flux0, 0, (size_t)c->rows * c->shape.groups_pad * sizeof(float), c->stream));
     }
     if ((rc = smk_reset_tallies(c)) != SMK_OK) return rc;
-    SMK_CUDA(cudaStreamSynchronize(c->stream));
+    // while the copies are in flight: bound tau = sigT * ds for the choice of the exponential's form
+    c->sigt_max = host_max(sigT, (int64_t)c->p.source_3D_regions * c->p.egroups);
     c->have_data = true;
+    return SMK_OK;
+}
+
+int smk_upload(smk_ctx *c, const float *fine_source, const float *fine_flux, const float *sigT)
+{
+    int rc = smk_upload_async(c, fine_source, fine_flux, sigT);
+    if (rc != SMK_OK) return rc;
+    SMK_CUDA(cudaStreamSynchronize(c->stream));
+    return SMK_OK;
+}
+
+int smk_upload_rows_async(smk_ctx *c, int array, int64_t row_begin, int64_t rows, const float *host)
+{
+    if (!c || !host) return fail(SMK_EINVAL, "NULL argument");
+    const int64_t total = (array == SMK_ARRAY_SIGT) ? c->p.source_3D_regions : c->rows;
+    if (array < SMK_ARRAY_SOURCE || array > SMK_ARRAY_SIGT) return fail(SMK_EINVAL, "unknown array %d", array);
+    if (row_begin < 0 || rows < 0 || row_begin + rows > total)
+        return fail(SMK_EINVAL, "rows [%lld, %lld) outside [0, %lld)", (long long)row_begin, (long long)(row_begin + rows),
+                    (long long)total);
+    SMK_CUDA(cudaSetDevice(c->p.device));
+    float *d = array == SMK_ARRAY_SOURCE ? c->d_source : array == SMK_ARRAY_FLUX ? c->d_flux0 : c->d_sigT;
+    int rc = upload_rows(c, host, d, row_begin, rows, array == SMK_ARRAY_SIGT ? 1.0f : 0.0f);
+    if (rc != SMK_OK) return rc;
+    if (array == SMK_ARRAY_SIGT) {
+        // a full-array upload keeps the bound exact; a partial one leaves the other rows unknown
+        c->sigt_max = (rows == total) ? host_max(host, rows * c->p.egroups) : INFINITY;
+    }
+    c->have_data = true;
+    return SMK_OK;
+}
+
+int smk_scan_sigt_max(smk_ctx *c, float *max_out)
+{
+    if (!c) return fail(SMK_EINVAL, "ctx is NULL");
+    SMK_CUDA(cudaSetDevice(c->p.device));
+    const int64_t n = (int64_t)c->p.source_3D_regions * c->shape.groups_pad;
+    SMK_CUDA(cudaMemsetAsync(c->d_max_bits, 0, sizeof(unsigned int), c->stream));
+    max_rows<<<layout_grid(n), 256, 0, c->stream>>>(c->d_sigT, n, c->d_max_bits);
+    SMK_CUDA(cudaGetLastError());
+    c->launches += 1;
+    unsigned int bits = 0;
+    SMK_CUDA(cudaMemcpyAsync(&bits, c->d_max_bits, sizeof bits, cudaMemcpyDeviceToHost, c->stream));
+    SMK_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(&c->sigt_max, &bits, sizeof bits);        // padding groups hold 1.0: the bound is >= 1 when G != G_pad
+    if (max_out) *max_out = c->sigt_max;
     return SMK_OK;
 }
 
@@ -494,6 +609,7 @@ int smk_fill_device(smk_ctx *c, float sigt_floor)
     int rc = smk_reset_tallies(c);
     if (rc != SMK_OK) return rc;
     SMK_CUDA(cudaStreamSynchronize(c->stream));
+    c->sigt_max = 1.0f;              // u01() < 1, padding = 1
     c->have_data = true;
     return SMK_OK;
 }
@@ -506,6 +622,8 @@ static int launch(smk_ctx *c, int64_t track_begin, int64_t track_end)
         return fail(SMK_EINVAL, "track range [%lld, %lld) outside [0, %lld)", (long long)track_begin,
                     (long long)track_end, (long long)c->n_tracks);
     SMK_CUDA(cudaSetDevice(c->p.device));
+    int rc = select_kernel(c);
+    if (rc != SMK_OK) return rc;
     c->last_begin = track_begin;
     c->last_end = track_end;
     const int64_t tracks = track_end - track_begin;
@@ -543,10 +661,15 @@ static int launch(smk_ctx *c, int64_t track_begin, int64_t track_end)
     a.fai_count = c->p.fine_axial_intervals;
     a.row_f4 = c->shape.groups_pad / 4;
     a.seg_per_track = c->p.seg_per_track;
+    a.group_blocks = c->shape.group_blocks;
+    a.geom = GeometryBase{c->geom.dz, c->geom.zin, c->geom.weight, c->geom.mu, c->geom.mu2, c->geom.ds, c->geom.spread};
+    const double dz = (double)c->geom.dz;
+    a.mesh = MeshConsts{(float)(1.0 / (2.0 * dz)), (float)(1.0 / (2.0 * dz * dz)), (float)(1.0 / dz)};
 
-    // persistent grid: a whole number of CTAs per SM, each track slot strides over tracks
+    // persistent grid: a whole number of CTAs per SM; warps claim work items dynamically
     const int slots_per_block = (kThreadsPerBlock / 32) * (32 / c->shape.lpt);
-    int64_t want = (tracks + slots_per_block - 1) / slots_per_block;
+    const int64_t work = tracks * c->shape.group_blocks;
+    int64_t want = (work + slots_per_block - 1) / slots_per_block;
     int64_t full = (int64_t)c->sm_count * c->blocks_per_sm;
     int grid = (int)(want < full ? want : full);
     c->kernel<<<grid, kThreadsPerBlock, c->dyn_smem, c->stream>>>(a);
@@ -585,28 +708,44 @@ int smk_run(smk_ctx *c, int64_t track_begin, int64_t track_end, double *kernel_s
 
 int64_t smk_launch_count(const smk_ctx *c) { return c ? c->launches : 0; }
 
-int smk_download_flux(smk_ctx *c, float *out)
+int smk_download_flux_rows_async(smk_ctx *c, int64_t row_begin, int64_t rows, float *out)
 {
     if (!c || !out) return fail(SMK_EINVAL, "NULL argument");
+    if (row_begin < 0 || rows < 0 || row_begin + rows > c->rows)
+        return fail(SMK_EINVAL, "rows [%lld, %lld) outside [0, %lld)", (long long)row_begin, (long long)(row_begin + rows),
+                    (long long)c->rows);
+    if (rows == 0) return SMK_OK;
     SMK_CUDA(cudaSetDevice(c->p.device));
     const int G = c->p.egroups, Gp = c->shape.groups_pad;
+    float *stage = c->d_stage + row_begin * G;
     if (c->d_tally64)
-        finalize_flux64<<<layout_grid(c->rows * G), 256, 0, c->stream>>>(c->d_flux0, c->d_tally64, c->d_stage, c->rows, G, Gp);
+        finalize_flux64<<<layout_grid(rows * G), 256, 0, c->stream>>>(c->d_flux0 + row_begin * Gp, c->d_tally64 + row_begin * Gp,
+                                                                     stage, rows, G, Gp);
     else
-        finalize_flux<<<layout_grid(c->rows * G), 256, 0, c->stream>>>(c->d_flux0, c->d_tally, c->d_stage, c->rows, G, Gp,
-                                                                     c->replicas);
+        finalize_flux<<<layout_grid(rows * G), 256, 0, c->stream>>>(c->d_flux0 + row_begin * Gp, c->d_tally + row_begin * Gp,
+                                                                   stage, rows, G, Gp, c->replicas, c->rows * Gp);
     SMK_CUDA(cudaGetLastError());
     c->launches += 1;
-    SMK_CUDA(cudaMemcpyAsync(out, c->d_stage, (size_t)c->rows * G * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    SMK_CUDA(cudaMemcpyAsync(out, stage, (size_t)rows * G * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    return SMK_OK;
+}
+
+int smk_download_flux(smk_ctx *c, float *out)
+{
+    if (!c) return fail(SMK_EINVAL, "NULL argument");
+    int rc = smk_download_flux_rows_async(c, 0, c->rows, out);
+    if (rc != SMK_OK) return rc;
     SMK_CUDA(cudaStreamSynchronize(c->stream));
     return SMK_OK;
 }
 
-int smk_download_psi(smk_ctx *c, float *psi_out)
+int smk_download_psi(smk_ctx *c, float *psi_out, int64_t n_tracks)
 {
     if (!c || !psi_out) return fail(SMK_EINVAL, "NULL argument");
     if (!(c->p.flags & SMK_FLAG_KEEP_PSI)) return fail(SMK_ESTATE, "context created without SMK_FLAG_KEEP_PSI");
     const int64_t tracks = c->last_end - c->last_begin;
+    if (n_tracks != tracks)
+        return fail(SMK_EINVAL, "psi_out holds %lld tracks but the last run swept %lld", (long long)n_tracks, (long long)tracks);
     if (tracks <= 0) return SMK_OK;
     SMK_CUDA(cudaSetDevice(c->p.device));
     SMK_CUDA(cudaMemcpy2DAsync(psi_out, (size_t)c->p.egroups * sizeof(float), c->d_psi,
@@ -635,11 +774,14 @@ int smk_run_host(const smk_params *p, const float *fine_source, float *fine_flux
     smk_ctx *c = nullptr;
     int rc = smk_create(p, &c);
     if (rc != SMK_OK) return rc;
-    cudaEvent_t t0, t1;
-    cudaEventCreate(&t0);
-    cudaEventCreate(&t1);
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (cudaEventCreate(&t0) != cudaSuccess || cudaEventCreate(&t1) != cudaSuccess) {
+        if (t0) cudaEventDestroy(t0);
+        smk_destroy(c);
+        return fail(SMK_ECUDA, "cudaEventCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     cudaEventRecord(t0, c->stream);
-    rc = smk_upload(c, fine_source, fine_flux, sigT);
+    rc = smk_upload_async(c, fine_source, fine_flux, sigT);
     if (rc == SMK_OK) rc = smk_run(c, 0, c->n_tracks, kernel_seconds);
     if (rc == SMK_OK) rc = smk_download_flux(c, fine_flux);
     if (rc == SMK_OK) {
@@ -803,8 +945,37 @@ int smk_multi_create(const smk_params *p, int n_devices, const int *devices, int
 int smk_multi_upload(smk_multi *m, const float *fine_source, const float *fine_flux, const float *sigT)
 {
     if (!m) return fail(SMK_EINVAL, "multi is NULL");
+    // one host -> device copy, to the first device ...
+    smk_ctx *c0 = m->ctx[0];
+    int rc = smk_upload_async(c0, fine_source, fine_flux, sigT);
+    if (rc != SMK_OK) return rc;
+    SMK_CUDA(cudaEventRecord(m->reduced[0], c0->stream));
+    // ... then every other device pulls the padded arrays over NVLink, all of them in parallel
+    const size_t slab = (size_t)c0->rows * c0->shape.groups_pad * sizeof(float);
+    const size_t sig = (size_t)c0->p.source_3D_regions * c0->shape.groups_pad * sizeof(float);
+    for (int d = 1; d < m->n; ++d) {
+        smk_ctx *c = m->ctx[d];
+        SMK_CUDA(cudaSetDevice(c->p.device));
+        SMK_CUDA(cudaStreamWaitEvent(c->stream, m->reduced[0], 0));
+        SMK_CUDA(cudaMemcpyPeerAsync(c->d_source, c->p.device, c0->d_source, c0->p.device, slab, c->stream));
+        SMK_CUDA(cudaMemcpyPeerAsync(c->d_sigT, c->p.device, c0->d_sigT, c0->p.device, sig, c->stream));
+        SMK_CUDA(cudaMemcpyPeerAsync(c->d_flux0, c->p.device, c0->d_flux0, c0->p.device, slab, c->stream));
+        if ((rc = smk_reset_tallies(c)) != SMK_OK) return rc;
+        c->sigt_max = c0->sigt_max;
+        c->have_data = true;
+    }
     for (int d = 0; d < m->n; ++d) {
-        int rc = smk_upload(m->ctx[d], fine_source, fine_flux, sigT);
+        SMK_CUDA(cudaSetDevice(m->ctx[d]->p.device));
+        SMK_CUDA(cudaStreamSynchronize(m->ctx[d]->stream));
+    }
+    return SMK_OK;
+}
+
+int smk_multi_set_geometry(smk_multi *m, const smk_geometry *g)
+{
+    if (!m) return fail(SMK_EINVAL, "multi is NULL");
+    for (int d = 0; d < m->n; ++d) {
+        int rc = smk_set_geometry(m->ctx[d], g);
         if (rc != SMK_OK) return rc;
     }
     return SMK_OK;
@@ -945,6 +1116,9 @@ int smk_debug_exp(int exp_mode, const float *tau, float *out, int64_t n, int dev
 {
     if (!tau || !out || n < 0) return fail(SMK_EINVAL, "bad argument");
     if (n == 0) return SMK_OK;
+    const bool packed = (exp_mode & SMK_DEBUG_EXP_PACKED) != 0, wide = (exp_mode & SMK_DEBUG_EXP_WIDE) != 0;
+    exp_mode &= 0xFF;
+    if (exp_mode < SMK_EXP_POLY || exp_mode > SMK_EXP_TABLE) return fail(SMK_EINVAL, "unknown exp_mode %d", exp_mode);
     SMK_CUDA(cudaSetDevice(device));
     ExpTable tab;
     build_exp_table(tab);
@@ -959,15 +1133,23 @@ int smk_debug_exp(int exp_mode, const float *tau, float *out, int64_t n, int dev
     }
     cudaMemcpy(d_in, tau, (size_t)n * sizeof(float), cudaMemcpyHostToDevice);
     const int grid = layout_grid(n);
-    switch (exp_mode) {
-        case SMK_EXP_POLY: debug_exp_kernel<kExpPoly><<<grid, 256>>>(d_in, d_out, n); break;
-        case SMK_EXP_MUFU: debug_exp_kernel<kExpMufu><<<grid, 256>>>(d_in, d_out, n); break;
-        case SMK_EXP_GLIBC: debug_exp_kernel<kExpGlibc><<<grid, 256>>>(d_in, d_out, n); break;
-        case SMK_EXP_TABLE: debug_exp_kernel<kExpTable><<<grid, 256>>>(d_in, d_out, n); break;
-        default:
-            cudaFree(d_in);
-            cudaFree(d_out);
-            return fail(SMK_EINVAL, "unknown exp_mode %d", exp_mode);
+    if (packed) {
+        switch (exp_mode) {
+            case SMK_EXP_POLY:
+                if (wide) debug_exp2_kernel<kExpPolyWide><<<grid, 256>>>(d_in, d_out, n);
+                else debug_exp2_kernel<kExpPoly><<<grid, 256>>>(d_in, d_out, n);
+                break;
+            case SMK_EXP_MUFU: debug_exp2_kernel<kExpMufu><<<grid, 256>>>(d_in, d_out, n); break;
+            case SMK_EXP_GLIBC: debug_exp2_kernel<kExpGlibc><<<grid, 256>>>(d_in, d_out, n); break;
+            case SMK_EXP_TABLE: debug_exp2_kernel<kExpTable><<<grid, 256>>>(d_in, d_out, n); break;
+        }
+    } else {
+        switch (exp_mode) {
+            case SMK_EXP_POLY: debug_exp_kernel<kExpPoly><<<grid, 256>>>(d_in, d_out, n); break;
+            case SMK_EXP_MUFU: debug_exp_kernel<kExpMufu><<<grid, 256>>>(d_in, d_out, n); break;
+            case SMK_EXP_GLIBC: debug_exp_kernel<kExpGlibc><<<grid, 256>>>(d_in, d_out, n); break;
+            case SMK_EXP_TABLE: debug_exp_kernel<kExpTable><<<grid, 256>>>(d_in, d_out, n); break;
+        }
     }
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy(out, d_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost);
@@ -977,30 +1159,50 @@ int smk_debug_exp(int exp_mode, const float *tau, float *out, int64_t n, int dev
     return SMK_OK;
 }
 
-int smk_debug_segment_ids(const smk_params *p, int64_t seg_begin, int64_t n, int32_t *qsr_out, int32_t *fai_out)
+static int debug_ids(const smk_params *p, const smk_geometry *g, int64_t seg_begin, int64_t n, int32_t *qsr_out,
+                     int32_t *fai_out, float *geom6_out)
 {
     Shape shape;
     int rc = validate(p, shape);
     if (rc != SMK_OK) return rc;
-    if (!qsr_out || !fai_out || n < 0 || seg_begin < 0) return fail(SMK_EINVAL, "bad argument");
+    if (n < 0 || seg_begin < 0) return fail(SMK_EINVAL, "bad argument");
     if (n == 0) return SMK_OK;
     SMK_CUDA(cudaSetDevice(p->device));
     int32_t *d_q = nullptr, *d_f = nullptr;
-    SMK_CUDA(cudaMalloc(&d_q, (size_t)n * sizeof(int32_t)));
-    cudaError_t e = cudaMalloc(&d_f, (size_t)n * sizeof(int32_t));
-    if (e != cudaSuccess) {
-        cudaFree(d_q);
-        return fail(SMK_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+    float *d_g = nullptr;
+    cudaError_t e = cudaMalloc(&d_q, (size_t)n * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_f, (size_t)n * sizeof(int32_t));
+    if (e == cudaSuccess && geom6_out) e = cudaMalloc(&d_g, (size_t)n * 6 * sizeof(float));
+    if (e == cudaSuccess) {
+        const smk_geometry gg = g ? *g : kReferenceGeometry;
+        debug_ids_kernel<<<layout_grid(n), 256>>>(p->seed, seg_begin, n, make_fastmod((uint32_t)p->source_3D_regions),
+                                                 make_fastmod((uint32_t)p->fine_axial_intervals),
+                                                 GeometryBase{gg.dz, gg.zin, gg.weight, gg.mu, gg.mu2, gg.ds, gg.spread},
+                                                 d_q, d_f, d_g);
+        e = cudaGetLastError();
     }
-    debug_ids_kernel<<<layout_grid(n), 256>>>(p->seed, seg_begin, n, make_fastmod((uint32_t)p->source_3D_regions),
-                                             make_fastmod((uint32_t)p->fine_axial_intervals), d_q, d_f);
-    e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpy(qsr_out, d_q, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(fai_out, d_f, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && qsr_out) e = cudaMemcpy(qsr_out, d_q, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && fai_out) e = cudaMemcpy(fai_out, d_f, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && geom6_out) e = cudaMemcpy(geom6_out, d_g, (size_t)n * 6 * sizeof(float), cudaMemcpyDeviceToHost);
     cudaFree(d_q);
     cudaFree(d_f);
+    cudaFree(d_g);
     if (e != cudaSuccess) return fail(SMK_ECUDA, "debug_segment_ids: %s", cudaGetErrorString(e));
     return SMK_OK;
+}
+
+int smk_debug_segment_ids(const smk_params *p, int64_t seg_begin, int64_t n, int32_t *qsr_out, int32_t *fai_out)
+{
+    if (!qsr_out || !fai_out) return fail(SMK_EINVAL, "bad argument");
+    return debug_ids(p, nullptr, seg_begin, n, qsr_out, fai_out, nullptr);
+}
+
+int smk_debug_segment_geometry(const smk_params *p, const smk_geometry *g, int64_t seg_begin, int64_t n, float *geom6_out)
+{
+    if (!geom6_out) return fail(SMK_EINVAL, "bad argument");
+    int rc = check_geometry(g);
+    if (rc != SMK_OK) return rc;
+    return debug_ids(p, g, seg_begin, n, nullptr, nullptr, geom6_out);
 }
 
 }  // extern "C"

@@ -10,10 +10,14 @@
 //           (kernel.c:236,249,251,291,301).  Throughput mode; checked against the
 //           oracle by the L2-relative gate of DESIGN.md section 6.
 //
-// Four evaluations of e = exp(-tau) (kernel.c:221), see exp_neg<>.
+// Four evaluations of e = exp(-tau) (kernel.c:221), see exp_val<>.
+// With GEOM (SMK_FLAG_SEGMENT_GEOMETRY) the six placeholder constants of kernel.c:99-104 are
+// per-segment values (smk_stream.cuh: segment_geometry) instead of literals.
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
+
+#include "smk_stream.cuh"
 
 namespace smk {
 
@@ -27,8 +31,16 @@ struct Geometry {
     static constexpr float ds = 0.7f;
 };
 
-enum : int { kExpPoly = 0, kExpMufu = 1, kExpGlibc = 2, kExpTable = 3 };
+// kExpPolyWide is internal: SMK_EXP_POLY when the data do not guarantee tau <= kPolyMaxTau
+enum : int { kExpPoly = 0, kExpMufu = 1, kExpGlibc = 2, kExpTable = 3, kExpPolyWide = 4 };
 enum : int { kMathFast = 0, kMathStrict = 1 };
+
+// exp_poly() is fitted on x = -tau in [-0.7, 0] (the reference's own data: sigT < 1, ds = 0.7).
+// Beyond that its error grows quickly (2e-6 at tau = 1, 9e-3 at tau = 2, garbage from tau = 3), so
+// for tau > kPolyMaxTau the POLY mode switches to MUFU.EX2: 1 - e is well conditioned there
+// (e <= 0.4966, so 2 ulp of e is 1.2e-7 of expVal) and the 1e-5 gate does not need the
+// correctly-rounded exponential that small tau needs.
+constexpr float kPolyMaxTau = 0.7f;
 
 // --------------------------------------------------------------------------
 // Exponential table of the reference (init.c:81-117): 353 {slope, intercept}
@@ -133,7 +145,7 @@ __device__ __forceinline__ float exp_val(float tau, const float2 *s_pairs, float
         return ev;
     } else {
         float e;
-        if constexpr (EXPM == kExpPoly) e = exp_poly(-tau);
+        if constexpr (EXPM == kExpPoly || EXPM == kExpPolyWide) e = (tau > kPolyMaxTau) ? exp_mufu(-tau) : exp_poly(-tau);
         else if constexpr (EXPM == kExpMufu) e = exp_mufu(-tau);
         else e = expf_glibc(-tau);
         e_out = e;
@@ -143,13 +155,19 @@ __device__ __forceinline__ float exp_val(float tau, const float2 *s_pairs, float
 
 // --------------------------------------------------------------------------
 // Quadratic / linear axial source fit (kernel.c:111-191) in difference form, constants folded
-// (dz = 0.1, zin = 0.3; q1, q2 pre-multiplied by mu, mu2):
+// (q1, q2 pre-multiplied by mu, mu2):
 //   d = y1 - y3,  s = y1 - 2 y2 + y3   with (y1, y2, y3) = fine_source[QSR][FAI-1 .. FAI+1][g]
 //   q0 = y2 + q0_d d + q0_s s,   mu q1 = q1_d d + q1_s s,   mu2 q2 = q2_s s
-//   interior   : ( 1.5,  4.5,  4.5, 27  , 15)   c1 = d / (2 dz), c2 = s / (2 dz^2)   (kernel.c:182-189)
-//   FAI == 0   : (-1.5,  1.5, -4.5,  4.5,  0)   with y1 := 0:  c1 = (y3 - y2) / dz   (kernel.c:128-134)
-//   FAI == F-1 : (-1.5, -1.5, -4.5, -4.5,  0)   with y3 := 0:  c1 = (y2 - y1) / dz   (kernel.c:154-160)
-// Per-lane coefficients are only needed where lanes of one warp serve tracks of different types.
+//   interior   : c1 = d / (2 dz), c2 = s / (2 dz^2)   (kernel.c:182-189)
+//       q0_d = zin/(2dz)  q0_s = zin^2/(2dz^2)  q1_d = mu/(2dz)  q1_s = mu zin/dz^2  q2_s = mu2/(2dz^2)
+//       = (1.5, 4.5, 4.5, 27, 15) for the reference geometry (dz = 0.1, zin = 0.3, mu = 0.9, mu2 = 0.3)
+//   FAI == 0   : c1 = (y3 - y2) / dz   (kernel.c:128-134):  q0 = y2 + e0 (y3 - y2), mu q1 = e1 (y3 - y2)
+//   FAI == F-1 : c1 = (y2 - y1) / dz   (kernel.c:154-160):  q0 = y2 + e0 (y2 - y1), mu q1 = e1 (y2 - y1)
+//       e0 = zin/dz = 3, e1 = mu/dz = 9
+// Per-lane coefficients (kFitDynamic) are needed where lanes of one warp serve tracks of different
+// types: the edge fits are then written in the interior's form with y1 := 0 or y3 := 0,
+//   FAI == 0   : (q0_d, q0_s, q1_d, q1_s, q2_s) = (-e0/2,  e0/2, -e1/2,  e1/2, 0)
+//   FAI == F-1 : (q0_d, q0_s, q1_d, q1_s, q2_s) = (-e0/2, -e0/2, -e1/2, -e1/2, 0)
 // --------------------------------------------------------------------------
 struct FitDiff {
     static constexpr float dz = Geometry::dz, zin = Geometry::zin, mu = Geometry::mu, mu2 = Geometry::mu2;
@@ -160,10 +178,19 @@ struct FitDiff {
     static constexpr float e0 = zin / dz, e1 = mu / dz;                     // 3, 9
 };
 
+// Per-segment scalars of the FAST arithmetic.  For a statically typed edge body (kFitFirst /
+// kFitLast) q0_d holds e0 and q1_d holds e1; the other fit fields are unused there.
 struct FitCoeffs {
     float q0_d, q0_s, q1_d, q1_s, q2_s;
+    float ds, weight;
 };
 
+// 1/(2dz), 1/(2dz^2), 1/dz of the problem's axial mesh (host-computed once)
+struct MeshConsts {
+    float k1, k2, inv_dz;
+};
+
+// reference geometry, per-lane segment type (sub-warp tracks)
 __device__ __forceinline__ FitCoeffs fit_coeffs(bool first, bool last)
 {
     const bool edge = first || last;
@@ -173,6 +200,48 @@ __device__ __forceinline__ FitCoeffs fit_coeffs(bool first, bool last)
     f.q1_d = edge ? -0.5f * FitDiff::e1 : FitDiff::q1_d;
     f.q1_s = first ? 0.5f * FitDiff::e1 : (last ? -0.5f * FitDiff::e1 : FitDiff::q1_s);
     f.q2_s = edge ? 0.0f : FitDiff::q2_s;
+    f.ds = Geometry::ds;
+    f.weight = Geometry::weight;
+    return f;
+}
+
+// per-segment geometry, coefficients in the interior's form for any type (kFitDynamic)
+__device__ __forceinline__ FitCoeffs fit_coeffs_geom(const SegGeometry &g, const MeshConsts &m, bool first, bool last)
+{
+    FitCoeffs f;
+    if (first || last) {
+        const float h0 = 0.5f * g.zin * m.inv_dz, h1 = 0.5f * g.mu * m.inv_dz;
+        f.q0_d = -h0;
+        f.q0_s = first ? h0 : -h0;
+        f.q1_d = -h1;
+        f.q1_s = first ? h1 : -h1;
+        f.q2_s = 0.0f;
+    } else {
+        const float kz = m.k2 * g.zin;
+        f.q0_d = m.k1 * g.zin;
+        f.q0_s = kz * g.zin;
+        f.q1_d = g.mu * m.k1;
+        f.q1_s = 2.0f * g.mu * kz;
+        f.q2_s = g.mu2 * m.k2;
+    }
+    f.ds = g.ds;
+    f.weight = g.weight;
+    return f;
+}
+
+// per-segment geometry, coefficients for the statically typed bodies (one track per warp: the
+// lane that hashed the segment computes them once, the warp shares them)
+__device__ __forceinline__ FitCoeffs fit_coeffs_geom_typed(const SegGeometry &g, const MeshConsts &m, bool edge)
+{
+    FitCoeffs f;
+    const float kz = m.k2 * g.zin;
+    f.q0_d = edge ? g.zin * m.inv_dz : m.k1 * g.zin;      // e0 | q0_d
+    f.q0_s = kz * g.zin;
+    f.q1_d = edge ? g.mu * m.inv_dz : g.mu * m.k1;        // e1 | q1_d
+    f.q1_s = 2.0f * g.mu * kz;
+    f.q2_s = g.mu2 * m.k2;
+    f.ds = g.ds;
+    f.weight = g.weight;
     return f;
 }
 
@@ -196,7 +265,7 @@ enum : int { kFitInterior = 0, kFitFirst = 1, kFitLast = 2, kFitDynamic = 3 };
 template <int EXPM>
 __device__ __forceinline__ float2 exp_val2(float2 tau, const float2 *s_pairs, float2 &e_out, float2 &tau2_out)
 {
-    if constexpr (EXPM == kExpPoly) {
+    if constexpr (EXPM == kExpPoly || EXPM == kExpPolyWide) {
         // exp_poly() on both halves, written in tau = -x: the odd coefficients change sign, every
         // intermediate is the same number up to sign, so e is bit-identical to exp_poly(-tau)
         float2 p = fma2(f2(-0x1.415ffep-13f), tau, f2(0x1.6336e4p-10f));
@@ -208,7 +277,16 @@ __device__ __forceinline__ float2 exp_val2(float2 tau, const float2 *s_pairs, fl
         tau2_out = x2;
         const float2 s = fma2(tau, f2(-1.0f), f2(1.0f));             // RN(1 - tau)
         const float2 lost = fma2(tau, f2(-1.0f), sub2(f2(1.0f), s)); // exact: (1 - tau) - s
-        const float2 e = add2(s, fma2(x2, p, lost));
+        float2 e = add2(s, fma2(x2, p, lost));
+        if constexpr (EXPM == kExpPolyWide) {
+            // outside the fitted range: MUFU.EX2 (XU pipe, otherwise idle), selected per half
+            const float2 t = mul2(tau, f2(-1.4426950408889634f));
+            float mx, my;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(mx) : "f"(t.x));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(my) : "f"(t.y));
+            e.x = (tau.x > kPolyMaxTau) ? mx : e.x;
+            e.y = (tau.y > kPolyMaxTau) ? my : e.y;
+        }
         e_out = e;
         return sub2(f2(1.0f), e);
     } else {
@@ -221,41 +299,34 @@ __device__ __forceinline__ float2 exp_val2(float2 tau, const float2 *s_pairs, fl
     }
 }
 
-// Two intersections.  FIT selects compile-time fit coefficients (edge types also skip the
-// quadratic terms, which are exactly zero there: q2 = 0, kernel.c:134,160) or, for
-// kFitDynamic, the per-lane coefficients in `f` (sub-warp tracks of different types).
-template <int EXPM, int FIT>
+// Two intersections.  FIT selects the segment type at compile time (the edge types also skip the
+// quadratic terms, which are exactly zero there: q2 = 0, kernel.c:134,160) or, for kFitDynamic,
+// per-lane coefficients in the interior's form.  The coefficients are literals for the reference
+// geometry with a static type and come from `f` otherwise (GEOM: per-segment geometry; kFitDynamic).
+template <int EXPM, int FIT, bool GEOM>
 __device__ __forceinline__ void attenuate_fast2(const FitCoeffs &f, float2 y1, float2 y2, float2 y3,
                                                 float2 sigT, const float2 *s_pairs, float2 &psi,
                                                 float2 &tally)
 {
     constexpr bool kQuadratic = (FIT == kFitInterior) || (FIT == kFitDynamic);
+    constexpr bool kFromF = GEOM || (FIT == kFitDynamic);
+    using K = FitDiff;
     float2 q0, Q1, Q2 = f2(0.0f);
-    if constexpr (FIT == kFitDynamic) {
-        const float2 d = sub2(y1, y3);
-        const float2 s = fma2(y2, f2(-2.0f), add2(y1, y3));
-        q0 = fma2(f2(f.q0_s), s, fma2(f2(f.q0_d), d, y2));
-        Q1 = fma2(f2(f.q1_s), s, mul2(f2(f.q1_d), d));
-        Q2 = mul2(f2(f.q2_s), s);
-    } else if constexpr (FIT == kFitInterior) {
+    if constexpr (kQuadratic) {
         // d = y1 - y3, s = y1 - 2 y2 + y3:  c1 = d / (2 dz), c2 = s / (2 dz^2)   (kernel.c:182-184)
-        using K = FitDiff;
         const float2 d = sub2(y1, y3);
         const float2 s = fma2(y2, f2(-2.0f), add2(y1, y3));
-        q0 = fma2(f2(K::q0_s), s, fma2(f2(K::q0_d), d, y2));       // y2 + c1 zin + c2 zin^2
-        Q1 = fma2(f2(K::q1_s), s, mul2(f2(K::q1_d), d));           // mu (c1 + 2 c2 zin)
-        Q2 = mul2(f2(K::q2_s), s);                                 // mu2 c2
-    } else if constexpr (FIT == kFitFirst) {
-        const float2 d = sub2(y3, y2);                             // c1 = (y3 - y2) / dz  (kernel.c:128)
-        q0 = fma2(f2(FitDiff::e0), d, y2);
-        Q1 = mul2(f2(FitDiff::e1), d);
+        q0 = fma2(f2(kFromF ? f.q0_s : K::q0_s), s, fma2(f2(kFromF ? f.q0_d : K::q0_d), d, y2));   // y2 + c1 zin + c2 zin^2
+        Q1 = fma2(f2(kFromF ? f.q1_s : K::q1_s), s, mul2(f2(kFromF ? f.q1_d : K::q1_d), d));        // mu (c1 + 2 c2 zin)
+        Q2 = mul2(f2(kFromF ? f.q2_s : K::q2_s), s);                                                // mu2 c2
     } else {
-        const float2 d = sub2(y2, y1);                             // c1 = (y2 - y1) / dz  (kernel.c:154)
-        q0 = fma2(f2(FitDiff::e0), d, y2);
-        Q1 = mul2(f2(FitDiff::e1), d);
+        // c1 = (y3 - y2) / dz (kernel.c:128) or (y2 - y1) / dz (kernel.c:154)
+        const float2 d = (FIT == kFitFirst) ? sub2(y3, y2) : sub2(y2, y1);
+        q0 = fma2(f2(GEOM ? f.q0_d : K::e0), d, y2);
+        Q1 = mul2(f2(GEOM ? f.q1_d : K::e1), d);
     }
 
-    const float2 tau = mul2(sigT, f2(Geometry::ds));
+    const float2 tau = mul2(sigT, f2(GEOM ? f.ds : Geometry::ds));
     float2 e, tau2;
     const float2 ev = exp_val2<EXPM>(tau, s_pairs, e, tau2);
     const float2 tme = sub2(tau, ev);                               // tau - expVal (exact)
@@ -272,27 +343,31 @@ __device__ __forceinline__ void attenuate_fast2(const FitCoeffs &f, float2 y1, f
     float2 fi = fma2(Q1, reuse, fma2(q0, Fc, mul2(psi, E)));
     float2 acc = mul2(psi, e);                                       // t4 = psi (1 - expVal), kernel.c:321
     if constexpr (kQuadratic) {
-        // tau (tau (tau - 3) + 6) - 6 expVal, kernel.c:250, evaluated in the reference's order and NOT
-        // contracted: its true value is ~tau^4/4 while its terms are ~6 tau, so for small sigT it is
-        // pure rounding noise (cancellation factor 24/tau^3) that, divided by 3 sigT^4, reaches 1e-4
-        // of the dominant term.  Parity needs the reference's own roundings here; measured (gpurun
-        // r01a, reproduced by CPU emulation): contracted 1.2e-4 L2-relative, reference order 3.6e-8.
+        // tau (tau (tau - 3) + 6) - 6 expVal, kernel.c:250, in the reference's order of operations: its true
+        // value is ~tau^4/4 while its terms are ~6 tau, so for small sigT it is pure rounding noise
+        // (cancellation factor 24/tau^3) that, divided by 3 sigT^4, reaches 1e-4 of the dominant term, and
+        // parity needs the reference's own roundings of the two large terms: 6 expVal is rounded before the
+        // subtraction (sub2 = fma(b, -1, a) adds nothing to that).  Measured (gpurun r01a, reproduced by
+        // CPU emulation): with the subtraction contracted into fma(-6, expVal, ...) 1.2e-4 L2-relative,
+        // this form 3.6e-8.  (ptxas does fuse tau (tau - 3) + 6 into one FFMA2; that rounding is below the
+        // noise floor of the term.)
         const float2 cubic = sub2(mul2(tau, add2(mul2(tau, add2(tau, f2(-3.0f))), f2(6.0f))),
                                   mul2(f2(6.0f), ev));
         fi = fma2(mul2(Q2, f2(1.0f / 3.0f)), mul2(cubic, mul2(rs2, rs2)), fi);         // kernel.c:250-251
         acc = fma2(Q2, reuse, acc);                                                     // t3, kernel.c:311
     }
-    tally = mul2(f2(Geometry::weight), fi);                          // kernel.c:262
+    tally = mul2(f2(GEOM ? f.weight : Geometry::weight), fi);        // kernel.c:262
     psi = fma2(q0, E, fma2(Q1, Fc, acc));                            // kernel.c:331
 }
 
-// STRICT: one intersection in the reference's own operation order.
+// STRICT: one intersection in the reference's own operation order; g holds kernel.c:99-104
+// (the literals for the reference geometry, the segment's values with GEOM).
 template <int EXPM>
-__device__ __forceinline__ void attenuate_strict(bool first, bool last, float y1, float y2,
+__device__ __forceinline__ void attenuate_strict(const SegGeometry &g, bool first, bool last, float y1, float y2,
                                                  float y3, float sigT, const float2 *s_pairs,
                                                  float &psi, float &tally)
 {
-    const float dz = Geometry::dz, zin = Geometry::zin, mu = Geometry::mu, mu2 = Geometry::mu2;
+    const float dz = g.dz, zin = g.zin, mu = g.mu, mu2 = g.mu2;
     float q0, q1, q2;
     if (first) {                                                    // kernel.c:111-135
         const float c1 = __fdiv_rn(__fsub_rn(y3, y2), dz);
@@ -313,7 +388,7 @@ __device__ __forceinline__ void attenuate_strict(bool first, bool last, float y1
         q1 = __fadd_rn(c1, __fmul_rn(__fmul_rn(2.0f, c2), zin));
         q2 = c2;
     }
-    const float tau = __fmul_rn(sigT, Geometry::ds);                // kernel.c:206
+    const float tau = __fmul_rn(sigT, g.ds);                        // kernel.c:206
     const float sigT2 = __fmul_rn(sigT, sigT);                      // kernel.c:207
     float e;
     const float ev = exp_val<EXPM>(tau, s_pairs, e);                // kernel.c:219/221
@@ -328,13 +403,18 @@ __device__ __forceinline__ void attenuate_strict(bool first, bool last, float y1
     const float term3 = __fdiv_rn(__fmul_rn(__fmul_rn(q2, mu2), cubic),
                                   __fmul_rn(__fmul_rn(3.0f, sigT2), sigT2));
     const float flux_integral = __fadd_rn(__fadd_rn(term1, term2), term3);  // kernel.c:248-251
-    tally = __fmul_rn(Geometry::weight, flux_integral);                     // kernel.c:262
+    tally = __fmul_rn(g.weight, flux_integral);                             // kernel.c:262
 
     const float t1 = __fdiv_rn(__fmul_rn(q0, ev), sigT);                               // :291
     const float t2 = __fdiv_rn(__fmul_rn(__fmul_rn(q1, mu), __fsub_rn(tau, ev)), sigT2);  // :301
     const float t3 = __fmul_rn(__fmul_rn(q2, mu2), reuse);                             // :311
     const float t4 = __fmul_rn(psi, __fsub_rn(1.0f, ev));                              // :321
     psi = __fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), t4);                             // :331
+}
+
+__device__ __forceinline__ SegGeometry reference_geometry()
+{
+    return SegGeometry{Geometry::dz, Geometry::zin, Geometry::weight, Geometry::mu, Geometry::mu2, Geometry::ds};
 }
 
 }  // namespace smk

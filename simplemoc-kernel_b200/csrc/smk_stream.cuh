@@ -144,6 +144,63 @@ SMK_HD uint32_t fastmod(uint32_t n, const FastMod &f)  // n < 2^31
     return n - q * f.d;
 }
 
+// --------------------------------------------------------------------------
+// Per-segment geometry (SMK_FLAG_SEGMENT_GEOMETRY).  kernel.c:95-104: "Some placeholder
+// constants - In the full app some of these are calculated based off position in geometry":
+// dz, zin, weight, mu, mu2, ds become parameters (smk_geometry) and, with the flag, vary per
+// segment.  Words 2,3 of the segment's stream block give four 16-bit fields u, each mapped to
+// a factor f(u) = 1 + spread * (u * 2^-15 - 1) in [1 - spread, 1 + spread):
+//   ds = ds0 f(w2 >> 16)       zin = zin0 f(w2 & 0xFFFF)
+//   mu = mu0 f(w3 >> 16)       mu2 = mu2_0 f(w3 >> 16)^2      weight = weight0 f(w3 & 0xFFFF)
+// dz (the axial mesh spacing) is the same for every segment.  Each step is ONE IEEE binary32
+// operation, never contracted, so host, oracle and every kernel derive bit-identical values;
+// spread = 0 gives f = 1 exactly, i.e. the base values.
+// --------------------------------------------------------------------------
+struct SegGeometry {
+    float dz, zin, weight, mu, mu2, ds;
+};
+
+struct GeometryBase {       // smk_geometry as the kernels take it
+    float dz, zin, weight, mu, mu2, ds, spread;
+};
+
+SMK_HD float geom_factor(uint32_t u16, float spread)
+{
+#if defined(__CUDA_ARCH__)
+    const float c = __fadd_rn(__fmul_rn((float)u16, 3.0517578125e-05f), -1.0f);   // u * 2^-15 - 1, exact
+    return __fadd_rn(1.0f, __fmul_rn(spread, c));
+#else
+    const float c = (float)u16 * 3.0517578125e-05f - 1.0f;
+    const float sc = spread * c;
+    return 1.0f + sc;
+#endif
+}
+
+SMK_HD float mul_rn(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+
+SMK_HD SegGeometry segment_geometry(const GeometryBase &b, uint32_t w2, uint32_t w3)
+{
+    const float f_ds = geom_factor(w2 >> 16, b.spread);
+    const float f_zin = geom_factor(w2 & 0xFFFFu, b.spread);
+    const float f_mu = geom_factor(w3 >> 16, b.spread);
+    const float f_w = geom_factor(w3 & 0xFFFFu, b.spread);
+    SegGeometry g;
+    g.dz = b.dz;
+    g.zin = mul_rn(b.zin, f_zin);
+    g.weight = mul_rn(b.weight, f_w);
+    g.mu = mul_rn(b.mu, f_mu);
+    g.mu2 = mul_rn(b.mu2, mul_rn(f_mu, f_mu));
+    g.ds = mul_rn(b.ds, f_ds);
+    return g;
+}
+
 struct SegmentIds { uint32_t qsr, fai; };
 
 SMK_HD SegmentIds segment_ids(const PhiloxKeys &ks, uint64_t seg, const FastMod &mod_regions,
@@ -157,7 +214,7 @@ SMK_HD SegmentIds segment_ids(uint64_t seed, uint64_t seg, const FastMod &mod_re
                               const FastMod &mod_fai)
 {
     u32x4 w = stream_words(seed, seg, 0u, kDomainSegment);
-    // words z, w are reserved for per-segment geometry (kernel.c:95-104)
+    // words z, w carry the per-segment geometry (segment_geometry above; kernel.c:95-104)
     return SegmentIds{fastmod(w.x >> 1, mod_regions), fastmod(w.y >> 1, mod_fai)};
 }
 

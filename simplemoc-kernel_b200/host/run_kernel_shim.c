@@ -18,6 +18,9 @@
  *
  * What changes for the user, by design of the north star: segments come from the deterministic counter
  * stream (seed SMK_SEED, default 42) instead of rand_r(), so the run is reproducible.
+ * The CPU driver has no -p / -d options (io.c:109-154), so segments per track and the device come from
+ * the environment (SMK_SEG_PER_TRACK, default 100 = the OpenMP chunk of kernel.c:43; SMK_DEVICE, default 0);
+ * -t only sizes the reference's OpenMP team, which the GPU sweep does not use.  All of this is printed.
  */
 #include "SimpleMOC-kernel_header.h"
 #include "smk.h"
@@ -30,7 +33,8 @@ void run_kernel(Input *I, Source *S, Table *table)
     p.source_3D_regions = I->source_3D_regions;      /* main.c:18-19 */
     p.fine_axial_intervals = I->fine_axial_intervals;
     p.egroups = I->egroups;
-    p.seg_per_track = 100;                            /* cuda init.cu:41 / the OpenMP chunk, kernel.c:43 */
+    const char *spt = getenv("SMK_SEG_PER_TRACK");
+    p.seg_per_track = spt ? atoi(spt) : 100;          /* cuda init.cu:41 / the OpenMP chunk, kernel.c:43 */
     p.segments = I->segments;
     const char *seed = getenv("SMK_SEED");
     p.seed = seed ? strtoull(seed, NULL, 10) : 42ull;
@@ -40,7 +44,10 @@ void run_kernel(Input *I, Source *S, Table *table)
     p.exp_mode = SMK_EXP_POLY;
 #endif
     p.math_mode = SMK_MATH_FAST;
-    p.device = 0;
+    const char *dev = getenv("SMK_DEVICE");
+    p.device = dev ? atoi(dev) : 0;
+    printf("GPU sweep on device %d: %d segments per track, stream seed %llu; -t %d is not used by the GPU path\n",
+           p.device, p.seg_per_track, (unsigned long long)p.seed, I->nthreads);
 
     /* initialize_sources lays the three slabs out contiguously from S[0] (init.c:35-54) */
     double kernel_s = 0.0, total_s = 0.0;

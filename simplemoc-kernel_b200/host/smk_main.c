@@ -38,6 +38,8 @@ typedef struct {
     int exp_mode, math_mode, device, gpus, allreduce;
     int host_fill;
     int tally_f64;
+    int segment_geometry;      /* kernel.c:99-104 vary per segment (SMK_FLAG_SEGMENT_GEOMETRY) */
+    float geometry_spread;
     float sigt_floor;
     const char *dump_flux;
     const char *verify_flux;   /* raw float32 flux of a CPU replay of the same stream */
@@ -111,6 +113,8 @@ static void usage_and_exit(void)
     puts("  --allreduce <impl>    peer (NVLink peer-memory kernel, default) | nccl");
     puts("  --host-fill           Fill the slabs on the host and upload them");
     puts("  --tally-f64           Diagnostic: accumulate the tallies in double precision");
+    puts("  --segment-geometry    dz, zin, weight, mu, mu2, ds vary per segment (stream words 2,3)");
+    puts("  --geometry-spread <x> Relative half-width of that variation, in [0, 1) (default 0.25)");
     puts("  --sigt-floor <x>      Well-conditioned diagnostic data: sigT in [x, 1)");
     puts("  --dump-flux <file>    Write the final scalar flux (raw float32)");
     puts("  --verify <file>       Compare the flux with a CPU replay of the same stream (raw float32,");
@@ -149,6 +153,7 @@ static void defaults(Input *I)
     I->exp_mode = SMK_EXP_POLY;
     I->math_mode = SMK_MATH_FAST;
     I->gpus = 1;
+    I->geometry_spread = 0.25f;
     I->tolerance = 1e-5;
 }
 
@@ -172,6 +177,8 @@ static void parse(int argc, char **argv, Input *I)
         else if (!strcmp(a, "--allreduce")) I->allreduce = lookup(need(argc, argv, &i), reduces, 2);
         else if (!strcmp(a, "--host-fill")) I->host_fill = 1;
         else if (!strcmp(a, "--tally-f64")) I->tally_f64 = 1;
+        else if (!strcmp(a, "--segment-geometry")) I->segment_geometry = 1;
+        else if (!strcmp(a, "--geometry-spread")) { I->geometry_spread = (float)atof(need(argc, argv, &i)); I->segment_geometry = 1; }
         else if (!strcmp(a, "--sigt-floor")) I->sigt_floor = (float)atof(need(argc, argv, &i));
         else if (!strcmp(a, "--dump-flux")) I->dump_flux = need(argc, argv, &i);
         else if (!strcmp(a, "--verify")) I->verify_flux = need(argc, argv, &i);
@@ -206,6 +213,8 @@ static void summary(const Input *I, const char *device_name)
     printf("%-25s%d\n", "Segments per CUDA block:", I->seg_per_thread);
     printf("%-25s%s\n", "Exponential Table:", I->exp_mode == SMK_EXP_TABLE ? "ON" : "OFF");
     printf("%-25s%llu\n", "Stream Seed:", I->seed);
+    if (I->segment_geometry)
+        printf("%-25sper segment, spread %.3f\n", "Segment Geometry:", I->geometry_spread);
     if (I->gpus > 1)
         printf("%-25s%d (%s all-reduce)\n", "GPUs:", I->gpus, I->allreduce == SMK_ALLREDUCE_NCCL ? "NCCL" : "peer-memory");
     rule();
@@ -278,12 +287,18 @@ int main(int argc, char *argv[])
     p.exp_mode = I.exp_mode;
     p.math_mode = I.math_mode;
     p.device = I.device;
-    p.flags = I.tally_f64 ? SMK_FLAG_TALLY_F64 : 0;
+    p.flags = (I.tally_f64 ? SMK_FLAG_TALLY_F64 : 0) | (I.segment_geometry ? SMK_FLAG_SEGMENT_GEOMETRY : 0);
 
     smk_ctx *ctx = NULL;
     smk_multi *multi = NULL;
     if (I.gpus > 1) CHECK(smk_multi_create(&p, I.gpus, NULL, I.allreduce, &multi));
     else CHECK(smk_create(&p, &ctx));
+    if (I.segment_geometry) {
+        /* base values = the reference's placeholders (kernel.c:99-104) */
+        smk_geometry g = {0.1f, 0.3f, 0.5f, 0.9f, 0.3f, 0.7f, I.geometry_spread};
+        if (multi) CHECK(smk_multi_set_geometry(multi, &g));
+        else CHECK(smk_set_geometry(ctx, &g));
+    }
     const long n_fine = (long)I.source_3D_regions * I.fine_axial_intervals * I.egroups;
     float *flux = (float *)malloc((size_t)n_fine * sizeof(float));
     if (!flux) { printf("Error: out of host memory\n"); return EXIT_FAILURE; }

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(smk):
     assert not missing, missing
     for f in declared_functions():
         assert getattr(smk.lib, f) is not None
-    assert smk.lib.smk_abi_version() == 1
+    assert smk.lib.smk_abi_version() == 2
 
 
 def test_no_torch_or_cuda_types_in_signatures():
@@ -39,11 +39,12 @@ def test_no_torch_or_cuda_types_in_signatures():
 
 
 def test_padded_groups(smk):
+    # G <= 128: next power of two of ceil(G/4) float4; beyond: whole blocks of 256 groups, any G
     want = {1: 4, 4: 4, 7: 8, 8: 8, 13: 16, 32: 32, 64: 64, 100: 128, 128: 128, 129: 256, 256: 256,
-            300: 512, 1024: 1024}
+            300: 512, 1024: 1024, 1025: 1280, 2000: 2048, 5000: 5120}
     for g, gp in want.items():
         assert smk.lib.smk_padded_groups(g) == gp
-    assert smk.lib.smk_padded_groups(0) < 0 and smk.lib.smk_padded_groups(1025) < 0
+    assert smk.lib.smk_padded_groups(0) < 0
     assert smk.lib.smk_num_tracks(1033, 37) == 28
     assert smk.lib.smk_num_tracks(0, 100) == 0
 
@@ -59,8 +60,9 @@ def test_input_defaults_match_reference(smk):
 
 def test_create_validates_before_touching_cuda(smk):
     h = C.c_void_p()
-    bad = [dict(source_3D_regions=0), dict(fine_axial_intervals=1), dict(egroups=0), dict(egroups=2000),
-           dict(seg_per_track=0), dict(segments=-1), dict(exp_mode=9), dict(math_mode=5)]
+    bad = [dict(source_3D_regions=0), dict(fine_axial_intervals=1), dict(egroups=0), dict(flags=64),
+           dict(seg_per_track=0), dict(segments=-1), dict(exp_mode=9), dict(math_mode=5),
+           dict(source_3D_regions=2 ** 24, egroups=2048)]        # row offsets would not fit 32 bits
     for kw in bad:
         base = dict(source_3D_regions=10, fine_axial_intervals=5, egroups=8, seg_per_track=10, segments=100,
                     seed=1, exp_mode=0, math_mode=0, device=0, flags=0)
@@ -119,6 +121,16 @@ def test_multi_and_misc_argument_validation(smk):
     assert smk.lib.smk_upload(None, None, None, None) == -1
     assert smk.lib.smk_run(None, 0, 0, None) == -1
     assert smk.lib.smk_download_flux(None, None) == -1
+    assert smk.lib.smk_download_psi(None, None, 0) == -1
+    assert smk.lib.smk_upload_async(None, None, None, None) == -1
+    assert smk.lib.smk_upload_rows_async(None, 0, 0, 0, None) == -1
+    assert smk.lib.smk_download_flux_rows_async(None, 0, 0, None) == -1
+    assert smk.lib.smk_set_geometry(None, None) == -1
+    assert smk.lib.smk_scan_sigt_max(None, None) == -1
+    assert smk.lib.smk_kernel_name(None) == b""
+    g = smk.Geometry(0.1, 0.3, 0.5, 0.9, 0.3, 0.7, 1.5)        # spread must be < 1
+    out = np.zeros((4, 6), np.float32)
+    assert smk.lib.smk_debug_segment_geometry(C.byref(p), C.byref(g), 0, 4, out) == -1
     assert smk.lib.smk_multi_run(None, None, None) == -1
     assert smk.lib.smk_launch_count(None) == 0
     assert smk.lib.smk_padded_elems(None) == 0

@@ -1,6 +1,11 @@
-"""GPU tests at BASELINE.json's FULL config-2 size (128 groups, 1e8 segments, 6750 regions x 5
-intervals, 100 segments per track) through size-independent properties -- the oracle would need
-~1 minute of all host cores for a full replay, so at this size we check:
+"""GPU tests at BASELINE.json's FULL sizes.
+
+Full parity (test_full_size_flux_parity): the GPU flux of configs 2, 3 and 4 -- the benchmarked FAST/POLY
+kernels and the STRICT/GLIBC verification kernels -- against a FULL CPU replay of the same 1e8 / 1e8 /
+1e7 segments by the oracle on all host cores (about 10 s of host time in total).
+
+Size-independent properties at config 2's size (128 groups, 1e8 segments, 6750 regions x 5 intervals,
+100 segments per track):
   * identical segment -> region indexing: the kernel's fingerprint over all 1e8 segments equals the
     one computed from the oracle's id stream
   * sub-sampled replay: in STRICT mode the outgoing psi of sampled track windows is BIT-EXACT
@@ -93,3 +98,47 @@ def test_full_size_additivity_and_repeatability(smk):
     # association error is a few 1e-6 .. 1e-5 norm-wise (hard part 2)
     assert l2rel(a + b - flux0, full) <= 5e-5
     assert np.isfinite(full).all()
+
+
+# ---------------------------------------------------------------------------------------
+# full parity at BASELINE sizes: GPU flux vs a full CPU replay of the same stream
+# ---------------------------------------------------------------------------------------
+FULL_CONFIGS = [
+    # id, 2D regions, G, segments, deep (few tally rows: gate on the f64 accumulators)
+    ("config2_128g_1e8", 5000, 128, 100_000_000, False),
+    ("config3_7g_1e8", 5000, 7, 100_000_000, False),
+    ("config4_64g_14regions_1e7", 10, 64, 10_000_000, True),
+]
+
+
+@pytest.mark.parametrize("name,r2d,groups,segments,deep", FULL_CONFIGS, ids=[c[0] for c in FULL_CONFIGS])
+def test_full_size_flux_parity(smk, oracle, name, r2d, groups, segments, deep):
+    """Scalar flux within 1e-5 (L2-relative, north star) of the CPU reference replay at the FULL size of
+    BASELINE configs 2, 3 and 4, identical segment -> region indexing, same finite pattern.  Config 4 puts
+    1.4e5 fp32 additions of mixed sign on each of its 4480 tally elements, so there the gate is applied to
+    the f64-accumulated results of both sides (arithmetic parity without an accumulation-order term) and
+    the fp32 atomics are checked against the GPU's own f64 result."""
+    from oracle.oracle import F64ACC
+    I = smk.Input(source_2D_regions=r2d, segments=segments, egroups=groups, seed=SEED).finalize()
+    Rr, Fr = I.source_3D_regions, I.fine_axial_intervals
+    src, flux0, sig = oracle.fill(Rr, Fr, groups, SEED)
+    want = flux0.copy()
+    _, chk_want = oracle.run(src, want, sig, segments, I.seg_per_thread, SEED, nthreads=0, flags=F64ACC if deep else 0)
+    for math_mode, exp_mode, tol in (("fast", "poly", 1e-5), ("strict", "glibc", 5e-6)):
+        I.math_mode, I.exp_mode, I.tally_f64 = math_mode, exp_mode, deep
+        with smk.Context(I) as ctx:
+            ctx.upload(src, flux0, sig)
+            ctx.run()
+            got, chk = ctx.download_flux(), ctx.checksum()
+        assert chk == chk_want, f"{name} {math_mode}: segment -> region indexing differs"
+        assert np.array_equal(np.isfinite(got), np.isfinite(want))
+        err = l2rel(got, want)
+        print(f"{name} {math_mode}/{exp_mode}: L2-rel {err:.3e}")
+        assert err <= tol, f"{name} {math_mode}/{exp_mode}: {err:.3e}"
+        if deep:
+            I.tally_f64 = False
+            with smk.Context(I) as ctx:
+                ctx.upload(src, flux0, sig)
+                ctx.run()
+                got32 = ctx.download_flux()
+            assert l2rel(got32, got) <= 1e-4
