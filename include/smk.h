@@ -151,6 +151,10 @@ int   smk_upload_async(smk_ctx *ctx, const float *fine_source, const float *fine
 int   smk_upload_rows_async(smk_ctx *ctx, int array, int64_t row_begin, int64_t rows, const float *host);
 /* max(sigT) of the device array (one small kernel + 4-byte read back; synchronises the stream) */
 int   smk_scan_sigt_max(smk_ctx *ctx, float *max_out);
+/* caller-supplied upper bound of sigT over ALL rows of the device array, for data the library did not
+ * see on the host (rows gathered from peers): e.g. the all-reduce(max) of the ranks' slice maxima.
+ * A bound that is too small makes SMK_EXP_POLY wrong for tau > 0.7; +inf is always safe. */
+int   smk_set_sigt_bound(smk_ctx *ctx, float bound);
 /* device-side deterministic fill, bit-identical to the host stream fill that
  * replaces init.c:64-75; sigt_floor = 0 for U[0,1) */
 int   smk_fill_device(smk_ctx *ctx, float sigt_floor);

@@ -92,7 +92,7 @@ ABI_SYMBOLS = (
     "smk_multi_device_count", "smk_multi_set_geometry",
     "smk_set_geometry", "smk_get_geometry", "smk_kernel_name", "smk_upload_async",
     "smk_upload_rows_async", "smk_scan_sigt_max", "smk_download_flux_rows_async",
-    "smk_debug_segment_geometry",
+    "smk_debug_segment_geometry", "smk_set_sigt_bound",
 )
 
 
@@ -128,6 +128,7 @@ def _load() -> C.CDLL:
     L.smk_upload_async.argtypes = [vp, vp, vp, vp]
     L.smk_upload_rows_async.argtypes = [vp, i32, i64, i64, vp]
     L.smk_scan_sigt_max.argtypes = [vp, C.POINTER(C.c_float)]
+    L.smk_set_sigt_bound.argtypes = [vp, C.c_float]
     L.smk_download_flux_rows_async.argtypes = [vp, i64, i64, vp]
     L.smk_multi_set_geometry.argtypes = [vp, C.POINTER(Geometry)]
     L.smk_debug_segment_geometry.argtypes = [C.POINTER(Params), C.POINTER(Geometry), i64, i64, _f32p]
@@ -287,6 +288,9 @@ class Context:
         v = C.c_float(0.0)
         _check(lib.smk_scan_sigt_max(self._h, C.byref(v)))
         return v.value
+
+    def set_sigt_bound(self, bound: float):
+        _check(lib.smk_set_sigt_bound(self._h, bound))
 
     def download_flux_rows_async(self, row_begin: int, rows: int, out):
         _check(lib.smk_download_flux_rows_async(self._h, row_begin, rows, self._ptr(out)))

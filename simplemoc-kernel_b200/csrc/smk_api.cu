@@ -594,6 +594,14 @@ int smk_scan_sigt_max(smk_ctx *c, float *max_out)
     return SMK_OK;
 }
 
+int smk_set_sigt_bound(smk_ctx *c, float bound)
+{
+    if (!c) return fail(SMK_EINVAL, "ctx is NULL");
+    if (!(bound >= 0.0f)) return fail(SMK_EINVAL, "bound must be >= 0 (or +inf)");
+    c->sigt_max = bound;
+    return SMK_OK;
+}
+
 int smk_fill_device(smk_ctx *c, float sigt_floor)
 {
     if (!c) return fail(SMK_EINVAL, "ctx is NULL");

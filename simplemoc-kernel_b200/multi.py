@@ -39,3 +39,40 @@ def all_reduce_tallies(tally, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(tally, op=dist.ReduceOp.SUM, group=group)
     return tally
+
+
+# ---------------------------------------------------------------------------------------------
+# end-to-end path with the host<->device traffic split over the ranks: every rank uploads 1/P of
+# the rows, the replicas are completed over NVLink, the tallies are reduced slice-wise to their
+# owners and every rank reads back 1/P of the flux.  Total PCIe traffic = 1x the data instead of Px.
+# ---------------------------------------------------------------------------------------------
+def shard_rows(n_rows: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous row range of `rank` (same partition rule as shard_tracks)."""
+    return shard_tracks(n_rows, rank, world)
+
+
+def gather_row_slices(full, n_rows: int, row_elems: int, world: int, group=None):
+    """all-gather with ragged slices: rank k broadcasts rows shard_rows(n_rows, k, world) of the flat
+    tensor `full` (n_rows * row_elems elements) to everybody, in place."""
+    import torch.distributed as dist
+    works = []
+    for k in range(world):
+        b, e = shard_rows(n_rows, k, world)
+        if e > b:
+            works.append(dist.broadcast(full[b * row_elems:e * row_elems], src=k, group=group, async_op=True))
+    for w in works:
+        w.wait()
+
+
+def reduce_row_slices(full, n_rows: int, row_elems: int, world: int, group=None):
+    """reduce-scatter with ragged, row-aligned slices: rows shard_rows(n_rows, k, world) of `full` are
+    summed onto rank k, in place (the other rows of a rank's tensor are left partially reduced)."""
+    import torch.distributed as dist
+    works = []
+    for k in range(world):
+        b, e = shard_rows(n_rows, k, world)
+        if e > b:
+            works.append(dist.reduce(full[b * row_elems:e * row_elems], dst=k, op=dist.ReduceOp.SUM, group=group,
+                                     async_op=True))
+    for w in works:
+        w.wait()
