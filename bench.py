@@ -226,13 +226,16 @@ def main_reference(a):
 # our arm
 # --------------------------------------------------------------------------------------
 def lane_ops_per_intersection(smk, egroups, F, geometry):
-    """FP32 lane-operations of the FAST/POLY arithmetic (csrc/smk_math.cuh): 46 per interior and 30 per edge
-    intersection where the segment type is warp-uniform (33..128 groups: one track per warp), 46 for every
-    intersection where tracks of different types share a warp (<= 32 groups) or rows are swept in blocks."""
+    """FP32 lane-operations of the FAST/POLY arithmetic (csrc/smk_math.cuh, counted in the SASS of the
+    default kernels: FFMA2 + FMUL2 + FADD2 per pair of groups): 45 per interior and 29 per edge
+    intersection where the segment type is warp-uniform (33..128 groups: one track per warp), 45 for every
+    intersection where tracks of different types share a warp (<= 32 groups) or rows are swept in blocks;
+    one more with per-segment geometry (the weight is applied per intersection instead of once at the end)."""
+    extra = 1.0 if geometry else 0.0
     gp = smk.lib.smk_padded_groups(egroups)
     if gp in (64, 128):
-        return (46.0 * (F - 2) + 30.0 * 2) / F
-    return 46.0
+        return ((45.0 + extra) * (F - 2) + (29.0 + extra) * 2) / F
+    return 45.0 + extra
 
 
 class Sweep:

@@ -198,7 +198,10 @@ int   smk_run_host(const smk_params *p, const float *fine_source,
 /* ---- plumbing for callers that own device memory (torch, NCCL) --------- */
 /* raw device pointers of the context's padded arrays (void* = float*) */
 void *smk_device_tally(smk_ctx *ctx);      /* [replicas][R][F][G_pad], the all-reduce operand;
-                                              replicas > 1 only when R*F < 4096 (contention relief) */
+                                              replicas > 1 only when R*F < 4096 (contention relief).
+                                              With SMK_MATH_FAST and the constant geometry the sums are
+                                              kept WITHOUT the segment weight (kernel.c:262; 0.5): the
+                                              download applies it once, bit-identically */
 void *smk_device_flux0(smk_ctx *ctx);      /* [R][F][G_pad] initial flux            */
 void *smk_device_source(smk_ctx *ctx);     /* [R][F][G_pad]                         */
 void *smk_device_sigT(smk_ctx *ctx);       /* [R][G_pad]                            */

@@ -726,12 +726,15 @@ int smk_download_flux_rows_async(smk_ctx *c, int64_t row_begin, int64_t rows, fl
     SMK_CUDA(cudaSetDevice(c->p.device));
     const int G = c->p.egroups, Gp = c->shape.groups_pad;
     float *stage = c->d_stage + row_begin * G;
+    // FAST kernels of the constant geometry leave the (constant) segment weight to this step
+    const bool unweighted = c->p.math_mode == kMathFast && !(c->p.flags & SMK_FLAG_SEGMENT_GEOMETRY);
+    const float scale = unweighted ? kTallyScaleConst : 1.0f;
     if (c->d_tally64)
         finalize_flux64<<<layout_grid(rows * G), 256, 0, c->stream>>>(c->d_flux0 + row_begin * Gp, c->d_tally64 + row_begin * Gp,
-                                                                     stage, rows, G, Gp);
+                                                                     stage, rows, G, Gp, scale);
     else
         finalize_flux<<<layout_grid(rows * G), 256, 0, c->stream>>>(c->d_flux0 + row_begin * Gp, c->d_tally + row_begin * Gp,
-                                                                   stage, rows, G, Gp, c->replicas, c->rows * Gp);
+                                                                   stage, rows, G, Gp, c->replicas, c->rows * Gp, scale);
     SMK_CUDA(cudaGetLastError());
     c->launches += 1;
     SMK_CUDA(cudaMemcpyAsync(out, stage, (size_t)rows * G * sizeof(float), cudaMemcpyDeviceToHost, c->stream));

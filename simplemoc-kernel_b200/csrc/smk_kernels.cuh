@@ -259,12 +259,22 @@ attenuate_warp_track(const KernelArgs a)
             }
             if constexpr (GEOM) __syncwarp();
             const int count = (nseg - b) < 32 ? (nseg - b) : 32;
+#ifdef SMK_PF_SIGT
+            // the sigT row heads the dependency chain (tau -> exp): fetch it one segment ahead
+            V st_next = LaneVec<GPL>::load(sigT + (__shfl_sync(kFull, my_sg, 0) | (uint32_t)lane));
+#endif
             for (int k = 0; k < count; ++k) {
                 const uint32_t pk = __shfl_sync(kFull, my_pk, k);
-                const uint32_t sg = __shfl_sync(kFull, my_sg, k);
                 const uint32_t idx = (pk & ~31u) | (uint32_t)lane;
                 const V *src = source + idx;
+#ifdef SMK_PF_SIGT
+                const V st = st_next;
+                const int kn = (k + 1 < count) ? k + 1 : k;
+                st_next = LaneVec<GPL>::load(sigT + (__shfl_sync(kFull, my_sg, kn) | (uint32_t)lane));
+#else
+                const uint32_t sg = __shfl_sync(kFull, my_sg, k);
                 const V st = LaneVec<GPL>::load(sigT + (sg | (uint32_t)lane));
+#endif
                 FitCoeffs fc = {};
                 if constexpr (GEOM) {
                     const float4 c0 = s_coef[warp][k][0], c1 = s_coef[warp][k][1];
@@ -455,11 +465,12 @@ __global__ void pad_rows(const float *__restrict__ src, float *__restrict__ dst,
     }
 }
 
-// out[row][G] = flux0[row][G_pad] + tally[row][G_pad]   (kernel.c:276 summed over the sweep), rows
-// [row_begin, row_begin + rows) of the arrays; `stride` = floats between tally replicas
+// out[row][G] = flux0[row][G_pad] + scale * tally[row][G_pad]   (kernel.c:276 summed over the sweep), rows
+// [row_begin, row_begin + rows) of the arrays; `stride` = floats between tally replicas; scale = the
+// segment weight where the kernel left it out (constant geometry, FAST), else 1
 __global__ void finalize_flux(const float *__restrict__ flux0, const float *__restrict__ tally,
                               float *__restrict__ out, int64_t rows, int groups, int groups_pad, int replicas,
-                              int64_t stride)
+                              int64_t stride, float scale)
 {
     const int64_t n = rows * groups;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -468,7 +479,7 @@ __global__ void finalize_flux(const float *__restrict__ flux0, const float *__re
         const int g = (int)(i - r * groups);
         float t = tally[r * groups_pad + g];
         for (int k = 1; k < replicas; ++k) t += tally[k * stride + r * groups_pad + g];
-        out[i] = flux0[r * groups_pad + g] + t;
+        out[i] = __fadd_rn(flux0[r * groups_pad + g], __fmul_rn(scale, t));
     }
 }
 
@@ -533,14 +544,14 @@ __global__ void allreduce_peer_slices(PeerArrays arrays, int n_dev, int64_t begi
 
 // out[row][G] = (float)(flux0 + tally64): finalize for the diagnostic f64 tallies
 __global__ void finalize_flux64(const float *__restrict__ flux0, const double *__restrict__ tally64,
-                                float *__restrict__ out, int64_t rows, int groups, int groups_pad)
+                                float *__restrict__ out, int64_t rows, int groups, int groups_pad, float scale)
 {
     const int64_t n = rows * groups;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / groups;
         const int g = (int)(i - r * groups);
-        out[i] = (float)((double)flux0[r * groups_pad + g] + tally64[r * groups_pad + g]);
+        out[i] = (float)((double)flux0[r * groups_pad + g] + (double)scale * tally64[r * groups_pad + g]);
     }
 }
 

@@ -272,9 +272,13 @@ __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b
 
 enum : int { kFitInterior = 0, kFitFirst = 1, kFitLast = 2, kFitDynamic = 3 };
 
-// e = exp(-tau) on both halves; returns expVal = 1 - e
+// what finalize_flux multiplies the summed FAST tallies of the constant geometry by (see attenuate_fast2)
+constexpr float kTallyScaleConst = Geometry::weight;
+
+// e = exp(-tau) on both halves; returns expVal = 1 - e.  omt_out = RN(1 - tau), a by-product of the
+// polynomial that attenuate_fast2 reuses for tau^2 - 2 tau = (1 - tau)^2 - 1.
 template <int EXPM>
-__device__ __forceinline__ float2 exp_val2(float2 tau, const float2 *s_pairs, float2 &e_out, float2 &tau2_out)
+__device__ __forceinline__ float2 exp_val2(float2 tau, const float2 *s_pairs, float2 &e_out, float2 &omt_out)
 {
     if constexpr (EXPM == kExpPoly || EXPM == kExpPolyWide) {
         // exp_poly() on both halves, written in tau = -x: the odd coefficients change sign, every
@@ -284,11 +288,14 @@ __device__ __forceinline__ float2 exp_val2(float2 tau, const float2 *s_pairs, fl
         p = fma2(p, tau, f2(0x1.555146p-5f));
         p = fma2(p, tau, f2(-0x1.555546p-3f));
         // leading coefficient: glibc's for small tau (see exp_poly), selected per half
+#ifdef SMK_EXPERIMENT_NO_GLIBC_TRACK   // timing experiment only: what the two selects cost
+        p = fma2(p, tau, f2(0.5f));
+#else
         p = fma2(p, tau, make_float2(tau.x < kPolyGlibcTau ? kPolyGlibcA2 : 0.5f,
                                      tau.y < kPolyGlibcTau ? kPolyGlibcA2 : 0.5f));
-        const float2 x2 = mul2(tau, tau);
-        tau2_out = x2;
+#endif
         const float2 s = fma2(tau, f2(-1.0f), f2(1.0f));             // RN(1 - tau)
+        omt_out = s;
         const float2 lost = fma2(tau, f2(-1.0f), sub2(f2(1.0f), s)); // exact: (1 - tau) - s
         float2 e = add2(s, fma2(tau, fma2(tau, p, f2(-kPolyGlibcB1)), lost));
         if constexpr (EXPM == kExpPolyWide) {
@@ -306,7 +313,7 @@ __device__ __forceinline__ float2 exp_val2(float2 tau, const float2 *s_pairs, fl
         float ex, ey;
         const float evx = exp_val<EXPM>(tau.x, s_pairs, ex);
         const float evy = exp_val<EXPM>(tau.y, s_pairs, ey);
-        tau2_out = mul2(tau, tau);
+        omt_out = fma2(tau, f2(-1.0f), f2(1.0f));
         e_out = make_float2(ex, ey);
         return make_float2(evx, evy);
     }
@@ -340,8 +347,8 @@ __device__ __forceinline__ void attenuate_fast2(const FitCoeffs &f, float2 y1, f
     }
 
     const float2 tau = mul2(sigT, f2(GEOM ? f.ds : Geometry::ds));
-    float2 e, tau2;
-    const float2 ev = exp_val2<EXPM>(tau, s_pairs, e, tau2);
+    float2 e, omt;
+    const float2 ev = exp_val2<EXPM>(tau, s_pairs, e, omt);
     const float2 tme = sub2(tau, ev);                               // tau - expVal (exact)
 
     const float2 rs = make_float2(rcp_mufu(sigT.x), rcp_mufu(sigT.y));
@@ -351,8 +358,10 @@ __device__ __forceinline__ void attenuate_fast2(const FitCoeffs &f, float2 y1, f
     // and the outgoing flux  t1 + t2 = q0 E + mu q1 Fc                              (kernel.c:291,301)
     const float2 E = mul2(ev, rs);
     const float2 Fc = mul2(tme, rs2);
-    // reuse = tau (tau - 2) + 2 expVal / sigT^3 = (tau^2 - 2 tau) + 2 E / sigT^2   (kernel.c:235-236)
-    const float2 reuse = fma2(f2(2.0f), mul2(E, rs2), fma2(tau, f2(-2.0f), tau2));
+    // reuse = tau (tau - 2) + 2 expVal / sigT^3 = ((1 - tau)^2 - 1) + 2 E / sigT^2   (kernel.c:235-236).
+    // (1 - tau) comes rounded from the exponential: 6e-8 absolute on a sum that is >= 0.5 (2 expVal / sigT^3
+    // >= 2 ds / sigT^2 - ..., while tau (tau - 2) >= -1), one operation instead of two.
+    const float2 reuse = fma2(f2(2.0f), mul2(E, rs2), fma2(omt, omt, f2(-1.0f)));
     float2 fi = fma2(Q1, reuse, fma2(q0, Fc, mul2(psi, E)));
     float2 acc = mul2(psi, e);                                       // t4 = psi (1 - expVal), kernel.c:321
     if constexpr (kQuadratic) {
@@ -369,7 +378,11 @@ __device__ __forceinline__ void attenuate_fast2(const FitCoeffs &f, float2 y1, f
         fi = fma2(mul2(Q2, f2(1.0f / 3.0f)), mul2(cubic, mul2(rs2, rs2)), fi);         // kernel.c:250-251
         acc = fma2(Q2, reuse, acc);                                                     // t3, kernel.c:311
     }
-    tally = mul2(f2(GEOM ? f.weight : Geometry::weight), fi);        // kernel.c:262
+    // kernel.c:262.  With the constant geometry the weight is the same for every segment and is applied once
+    // to the summed tallies by finalize_flux (kTallyScaleConst; 0.5 is a power of two, so the result is
+    // bit-identical to weighting every contribution); per-segment weights are applied here.
+    if constexpr (GEOM) tally = mul2(f2(f.weight), fi);
+    else tally = fi;
     psi = fma2(q0, E, fma2(Q1, Fc, acc));                            // kernel.c:331
 }
 

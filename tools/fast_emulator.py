@@ -65,7 +65,7 @@ def exp_poly_neg(tau, track_glibc=True):
     else:
         p = fma(p, tau, f32(0.5))
         e = add(s, fma(x2, p, lost))
-    return e, x2
+    return e, x2, s
 
 
 def attenuate_fast(kind, fc, y1, y2, y3, sigT, psi, variant="cur"):
@@ -89,17 +89,21 @@ def attenuate_fast(kind, fc, y1, y2, y3, sigT, psi, variant="cur"):
     Q2 = np.where(interior, Q2_i, f32(0.0))
 
     tau = mul(sigT, fc["ds"])
-    e, tau2 = exp_poly_neg(tau)
+    e, tau2, one_m_tau = exp_poly_neg(tau)
     ev = sub(f32(1.0), e)
     tme = sub(tau, ev)
     rs = rcp(sigT)
     rs2 = mul(rs, rs)
     E = mul(ev, rs)
     Fc = mul(tme, rs2)
-    reuse = fma(f32(2.0), mul(E, rs2), fma(tau, f32(-2.0), tau2))
+    if variant == "old_reuse":
+        reuse = fma(f32(2.0), mul(E, rs2), fma(tau, f32(-2.0), tau2))
+    else:
+        # tau^2 - 2 tau = (1 - tau)^2 - 1 from the exponential's s = RN(1 - tau): one operation
+        reuse = fma(f32(2.0), mul(E, rs2), fma(one_m_tau, one_m_tau, f32(-1.0)))
     fi = fma(Q1, reuse, fma(q0, Fc, mul(psi, E)))
     acc = mul(psi, e)
-    if variant == "cur":
+    if variant in ("cur", "old_reuse"):
         cubic = sub(mul(tau, fma(tau, add(tau, f32(-3.0)), f32(6.0))), mul(f32(6.0), ev))   # as ptxas fuses it
     elif variant == "nofuse":
         cubic = sub(mul(tau, add(mul(tau, add(tau, f32(-3.0))), f32(6.0))), mul(f32(6.0), ev))
