@@ -245,9 +245,12 @@ int   smk_multi_device_count(const smk_multi *m);
 /* ---- diagnostics ------------------------------------------------------- */
 /* d_out[i] = exp(-tau[i]) as evaluated by exp_mode (host arrays, n elements);
  * used to sweep the exponential against libm.  exp_mode | SMK_DEBUG_EXP_PACKED evaluates the
- * packed (FP32x2) form of the FAST kernels; SMK_DEBUG_EXP_WIDE selects POLY's wide-range form */
+ * packed (FP32x2) form of the FAST kernels; SMK_DEBUG_EXP_WIDE selects POLY's wide-range form,
+ * SMK_DEBUG_EXP_TRACK its libm-following form (the scalar POLY of SMK_MATH_STRICT always follows libm) */
 #define SMK_DEBUG_EXP_PACKED 0x100
 #define SMK_DEBUG_EXP_WIDE   0x200
+#define SMK_DEBUG_EXP_TRACK  0x400   /* packed POLY as the per-segment-geometry kernels evaluate it: follows
+                                        glibc's expf where that is not correctly rounded (tau < 2^-8) */
 int   smk_debug_exp(int exp_mode, const float *tau, float *out, int64_t n, int device);
 /* (QSR_id, FAI_id) of segments [seg_begin, seg_begin+n) as the kernel draws them */
 int   smk_debug_segment_ids(const smk_params *p, int64_t seg_begin, int64_t n,

@@ -34,7 +34,7 @@ FLAG_KEEP_PSI = 1
 FLAG_TALLY_F64 = 2
 FLAG_SEGMENT_GEOMETRY = 4
 ARRAY_SOURCE, ARRAY_FLUX, ARRAY_SIGT = 0, 1, 2
-DEBUG_EXP_PACKED, DEBUG_EXP_WIDE = 0x100, 0x200
+DEBUG_EXP_PACKED, DEBUG_EXP_WIDE, DEBUG_EXP_TRACK = 0x100, 0x200, 0x400
 # kernel.c:99-104: dz, zin, weight, mu, mu2, ds
 REFERENCE_GEOMETRY = (0.1, 0.3, 0.5, 0.9, 0.3, 0.7)
 
@@ -416,12 +416,15 @@ def run_kernel(I: Input, fine_source: np.ndarray, fine_flux: np.ndarray, sigT: n
     return ks.value, ts.value
 
 
-def debug_exp(exp_mode: str, tau: np.ndarray, device: int = 0, packed: bool = False, wide: bool = False) -> np.ndarray:
+def debug_exp(exp_mode: str, tau: np.ndarray, device: int = 0, packed: bool = False, wide: bool = False,
+              track: bool = False) -> np.ndarray:
     """exp(-tau) as the kernels evaluate it; packed = the FP32x2 form of the FAST kernels,
-    wide = POLY's wide-range form (MUFU.EX2 beyond tau = 0.7)."""
+    wide = POLY's wide-range form (MUFU.EX2 beyond tau = 0.7), track = the packed form of the
+    per-segment-geometry kernels (follows libm where libm is not correctly rounded)."""
     tau = np.ascontiguousarray(tau, np.float32)
     out = np.empty_like(tau)
-    mode = EXP_MODES[exp_mode] | (DEBUG_EXP_PACKED if packed else 0) | (DEBUG_EXP_WIDE if wide else 0)
+    mode = EXP_MODES[exp_mode] | (DEBUG_EXP_PACKED if packed else 0) | (DEBUG_EXP_WIDE if wide else 0) | \
+        (DEBUG_EXP_TRACK if track else 0)
     _check(lib.smk_debug_exp(mode, tau, out, tau.size, device))
     return out
 

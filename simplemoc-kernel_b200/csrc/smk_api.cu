@@ -1128,6 +1128,7 @@ int smk_debug_exp(int exp_mode, const float *tau, float *out, int64_t n, int dev
     if (!tau || !out || n < 0) return fail(SMK_EINVAL, "bad argument");
     if (n == 0) return SMK_OK;
     const bool packed = (exp_mode & SMK_DEBUG_EXP_PACKED) != 0, wide = (exp_mode & SMK_DEBUG_EXP_WIDE) != 0;
+    const bool track = (exp_mode & SMK_DEBUG_EXP_TRACK) != 0;
     exp_mode &= 0xFF;
     if (exp_mode < SMK_EXP_POLY || exp_mode > SMK_EXP_TABLE) return fail(SMK_EINVAL, "unknown exp_mode %d", exp_mode);
     SMK_CUDA(cudaSetDevice(device));
@@ -1147,12 +1148,14 @@ int smk_debug_exp(int exp_mode, const float *tau, float *out, int64_t n, int dev
     if (packed) {
         switch (exp_mode) {
             case SMK_EXP_POLY:
-                if (wide) debug_exp2_kernel<kExpPolyWide><<<grid, 256>>>(d_in, d_out, n);
-                else debug_exp2_kernel<kExpPoly><<<grid, 256>>>(d_in, d_out, n);
+                if (wide && track) debug_exp2_kernel<kExpPolyWide, true><<<grid, 256>>>(d_in, d_out, n);
+                else if (wide) debug_exp2_kernel<kExpPolyWide, false><<<grid, 256>>>(d_in, d_out, n);
+                else if (track) debug_exp2_kernel<kExpPoly, true><<<grid, 256>>>(d_in, d_out, n);
+                else debug_exp2_kernel<kExpPoly, false><<<grid, 256>>>(d_in, d_out, n);
                 break;
-            case SMK_EXP_MUFU: debug_exp2_kernel<kExpMufu><<<grid, 256>>>(d_in, d_out, n); break;
-            case SMK_EXP_GLIBC: debug_exp2_kernel<kExpGlibc><<<grid, 256>>>(d_in, d_out, n); break;
-            case SMK_EXP_TABLE: debug_exp2_kernel<kExpTable><<<grid, 256>>>(d_in, d_out, n); break;
+            case SMK_EXP_MUFU: debug_exp2_kernel<kExpMufu, false><<<grid, 256>>>(d_in, d_out, n); break;
+            case SMK_EXP_GLIBC: debug_exp2_kernel<kExpGlibc, false><<<grid, 256>>>(d_in, d_out, n); break;
+            case SMK_EXP_TABLE: debug_exp2_kernel<kExpTable, false><<<grid, 256>>>(d_in, d_out, n); break;
         }
     } else {
         switch (exp_mode) {

@@ -580,8 +580,9 @@ __global__ void debug_exp_kernel(const float *__restrict__ tau, float *__restric
     }
 }
 
-// the packed FAST exponential as the hot kernels evaluate it (both halves get the same tau)
-template <int EXPM>
+// the packed FAST exponential as the hot kernels evaluate it (both halves get the same tau); TRACK = the
+// form of the per-segment-geometry kernels
+template <int EXPM, bool TRACK>
 __global__ void debug_exp2_kernel(const float *__restrict__ tau, float *__restrict__ out, int64_t n)
 {
     __shared__ float2 s_pairs[kTableReach];
@@ -590,7 +591,7 @@ __global__ void debug_exp2_kernel(const float *__restrict__ tau, float *__restri
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         float2 e, t2;
-        (void)exp_val2<EXPM>(f2(tau[i]), s_pairs, e, t2);
+        (void)exp_val2<EXPM, TRACK>(f2(tau[i]), s_pairs, e, t2);
         out[i] = e.x;
     }
 }

@@ -277,7 +277,12 @@ constexpr float kTallyScaleConst = Geometry::weight;
 
 // e = exp(-tau) on both halves; returns expVal = 1 - e.  omt_out = RN(1 - tau), a by-product of the
 // polynomial that attenuate_fast2 reuses for tau^2 - 2 tau = (1 - tau)^2 - 1.
-template <int EXPM>
+// TRACK selects the glibc-following leading coefficient per half (see exp_poly): two FSETP + two FSEL per pair,
+// 4 % of the 128-group kernel's time (profiles/ab_r02.md).  The kernels switch it on with per-segment
+// geometry, where every intersection draws its own tau; with the constant geometry tau takes one value per
+// (region, group), libm's misroundings (2e-5 of the values at tau = 5e-4) hit an element that matters with
+// probability ~1e-4 per data set, and the selects are left out.
+template <int EXPM, bool TRACK>
 __device__ __forceinline__ float2 exp_val2(float2 tau, const float2 *s_pairs, float2 &e_out, float2 &omt_out)
 {
     if constexpr (EXPM == kExpPoly || EXPM == kExpPolyWide) {
@@ -288,12 +293,11 @@ __device__ __forceinline__ float2 exp_val2(float2 tau, const float2 *s_pairs, fl
         p = fma2(p, tau, f2(0x1.555146p-5f));
         p = fma2(p, tau, f2(-0x1.555546p-3f));
         // leading coefficient: glibc's for small tau (see exp_poly), selected per half
-#ifdef SMK_EXPERIMENT_NO_GLIBC_TRACK   // timing experiment only: what the two selects cost
-        p = fma2(p, tau, f2(0.5f));
-#else
-        p = fma2(p, tau, make_float2(tau.x < kPolyGlibcTau ? kPolyGlibcA2 : 0.5f,
-                                     tau.y < kPolyGlibcTau ? kPolyGlibcA2 : 0.5f));
-#endif
+        if constexpr (TRACK)
+            p = fma2(p, tau, make_float2(tau.x < kPolyGlibcTau ? kPolyGlibcA2 : 0.5f,
+                                         tau.y < kPolyGlibcTau ? kPolyGlibcA2 : 0.5f));
+        else
+            p = fma2(p, tau, f2(0.5f));
         const float2 s = fma2(tau, f2(-1.0f), f2(1.0f));             // RN(1 - tau)
         omt_out = s;
         const float2 lost = fma2(tau, f2(-1.0f), sub2(f2(1.0f), s)); // exact: (1 - tau) - s
@@ -348,7 +352,7 @@ __device__ __forceinline__ void attenuate_fast2(const FitCoeffs &f, float2 y1, f
 
     const float2 tau = mul2(sigT, f2(GEOM ? f.ds : Geometry::ds));
     float2 e, omt;
-    const float2 ev = exp_val2<EXPM>(tau, s_pairs, e, omt);
+    const float2 ev = exp_val2<EXPM, GEOM>(tau, s_pairs, e, omt);
     const float2 tme = sub2(tau, ev);                               // tau - expVal (exact)
 
     const float2 rs = make_float2(rcp_mufu(sigT.x), rcp_mufu(sigT.y));

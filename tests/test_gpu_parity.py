@@ -430,8 +430,17 @@ def test_poly_wide_range_exponential(smk, oracle):
     rng = np.random.default_rng(3)
     tau_in = np.exp(rng.uniform(np.log(2.0 ** -31), np.log(0.7), 500_000)).astype(np.float32)
     scalar = smk.debug_exp("poly", tau_in)
-    assert np.array_equal(bits(smk.debug_exp("poly", tau_in, packed=True)), bits(scalar))
-    assert np.array_equal(bits(smk.debug_exp("poly", tau_in, packed=True, wide=True)), bits(scalar))
+    # the libm-following packed form (per-segment-geometry kernels) is the scalar polynomial bit for bit
+    assert np.array_equal(bits(smk.debug_exp("poly", tau_in, packed=True, track=True)), bits(scalar))
+    assert np.array_equal(bits(smk.debug_exp("poly", tau_in, packed=True, wide=True, track=True)), bits(scalar))
+    # the constant-geometry kernels leave the per-half select out: identical from tau = 2^-8 up, and below
+    # that within one ulp on a few 1e-4 of the values (exactly where libm is not correctly rounded)
+    plain = smk.debug_exp("poly", tau_in, packed=True)
+    assert np.array_equal(bits(smk.debug_exp("poly", tau_in, packed=True, wide=True)), bits(plain))
+    big = tau_in >= np.float32(2.0 ** -8)
+    assert np.array_equal(bits(plain[big]), bits(scalar[big]))
+    d = np.abs(bits(plain[~big]).astype(np.int64) - bits(scalar[~big]).astype(np.int64))
+    assert d.max() <= 1 and np.mean(d != 0) <= 1e-3
     tau_out = np.concatenate([np.nextafter(np.float32(0.7), np.float32(1.0), dtype=np.float32)[None],
                               rng.uniform(0.7, 80.0, 500_000).astype(np.float32)])
     tau_out = tau_out[tau_out > np.float32(0.7)]
@@ -454,8 +463,11 @@ def test_poly_follows_libm_for_small_tau(smk, oracle):
         tau = np.exp2(rng.uniform(lo, hi, 2_000_000)).astype(np.float32)
         ref = oracle.expf_neg(tau)
         for packed in (False, True):
-            got = smk.debug_exp("poly", tau, packed=packed)
+            got = smk.debug_exp("poly", tau, packed=packed, track=packed)
             assert np.mean(bits(got) != bits(ref)) <= allowed, (lo, hi, packed)
+    # without the select (constant geometry): correctly rounded, hence off only where libm is
+    tau = np.exp2(rng.uniform(-40.0, -14.0, 2_000_000)).astype(np.float32)
+    assert np.array_equal(bits(smk.debug_exp("poly", tau, packed=True)), bits(oracle.expf_neg(tau)))
 
 
 @pytest.mark.parametrize("R,F,G,N,p,seed", [(100, 5, 128, 50_000, 100, 81), (100, 5, 64, 50_000, 100, 82),
