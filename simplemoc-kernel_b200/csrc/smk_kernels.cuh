@@ -195,6 +195,7 @@ __device__ __forceinline__ void tally_lane(float *tally, double *tally64, uint32
 }
 
 constexpr uint32_t kPkFirst = 1u, kPkLast = 2u;
+constexpr uint32_t kRowFirst = 1u << 30, kRowLast = 1u << 31;     // general kernel: flags above the row index
 
 template <int GPL, int EXPM, bool F64, bool GEOM>
 __global__ void __launch_bounds__(kThreadsPerBlock, GEOM ? kMinBlocksGeom : kMinBlocksFast)
@@ -339,7 +340,9 @@ attenuate_tracks(const KernelArgs a)
     const int64_t warp_global = (int64_t)blockIdx.x * (kThreadsPerBlock / 32) + (threadIdx.x >> 5);
 
     const int F = a.fai_count;
-    const int row_f4 = a.row_f4;
+    // sub-warp tracks: a padded row is exactly one group block, so its size is a compile-time constant
+    // (row offsets become shifts and the neighbouring rows immediate offsets instead of FMA-pipe IMADs)
+    const int row_f4 = (LPT < 32) ? kBlockF4 : a.row_f4;
     const int p = a.seg_per_track;
     const int nblk = (LPT == 32) ? a.group_blocks : 1;
     float *const tally = warp_tally(a, warp_global);
@@ -371,12 +374,15 @@ attenuate_tracks(const KernelArgs a)
 
         for (int b = 0; b < nseg_warp; b += LPT) {
             // each lane of the track draws the ids of one of the next LPT segments
-            uint32_t my_qsr = 0u, my_fai = 0u, my_w2 = 0u, my_w3 = 0u;
+            // packed: row = QSR_id * F + FAI_id (< 2^29: smk_create checks R * F * G_pad / 4 < 2^31), first / last flags
+            uint32_t my_qsr = 0u, my_row = 0u, my_w2 = 0u, my_w3 = 0u;
             if (b + sub < nseg) {
                 const uint64_t seg = (uint64_t)(s0 + b + sub);
                 const u32x4 w = stream_words(a.keys, seg, 0u, kDomainSegment);
                 my_qsr = fastmod(w.x >> 1, a.mod_regions);                   // kernel.c:47
-                my_fai = fastmod(w.y >> 1, a.mod_fai);                       // kernel.c:50
+                const uint32_t my_fai = fastmod(w.y >> 1, a.mod_fai);        // kernel.c:50
+                my_row = (my_qsr * (uint32_t)F + my_fai) | (my_fai == 0u ? kRowFirst : 0u) |
+                         (my_fai == (uint32_t)(F - 1) ? kRowLast : 0u);
                 my_w2 = w.z;
                 my_w3 = w.w;
                 if (blk == 0) checksum += checksum_term(my_qsr, my_fai, (uint32_t)F, seg);
@@ -384,13 +390,12 @@ attenuate_tracks(const KernelArgs a)
             const int count = (nseg_warp - b) < LPT ? (nseg_warp - b) : LPT;
             for (int k = 0; k < count; ++k) {
                 const uint32_t qsr = __shfl_sync(kFull, my_qsr, k, LPT);
-                const uint32_t fai = __shfl_sync(kFull, my_fai, k, LPT);
+                const uint32_t prow = __shfl_sync(kFull, my_row, k, LPT);
                 // only the stream's ragged last track can be shorter than its warp-mates
                 const bool active = (LPT == 32) ? true : (b + k) < nseg;
-                const bool first = (fai == 0u);
-                const bool last = (fai == (uint32_t)(F - 1));
-                // 32-bit row offsets (smk_create checks R * F * G_pad / 4 < 2^31)
-                const uint32_t row = qsr * (uint32_t)F + fai;
+                const bool first = (prow & kRowFirst) != 0u;
+                const bool last = (prow & kRowLast) != 0u;
+                const uint32_t row = prow & ~(kRowFirst | kRowLast);
                 const uint32_t off = row * (uint32_t)row_f4 + (uint32_t)(boff + sub);
                 const float4 *src = a.source + off;
                 const float4 *sig = a.sigT + (qsr * (uint32_t)row_f4 + (uint32_t)(boff + sub));
