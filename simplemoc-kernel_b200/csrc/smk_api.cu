@@ -253,6 +253,8 @@ static int validate(const smk_params *p, Shape &shape)
     if (!shape_for(p->egroups, shape)) return fail(SMK_EINVAL, "egroups = %d unsupported", p->egroups);
     if ((int64_t)p->source_3D_regions * p->fine_axial_intervals * (shape.groups_pad / 4) >= (1ll << 31))
         return fail(SMK_EINVAL, "regions * intervals * padded groups / 4 must be < 2^31 (32-bit row offsets)");
+    if (p->source_3D_regions >= (1 << 25))
+        return fail(SMK_EINVAL, "regions must be < 2^25 (sigT row index + two flag bits in one word)");
     if ((int64_t)p->source_3D_regions * p->fine_axial_intervals >= (1ll << 30))
         return fail(SMK_EINVAL, "regions * intervals must be < 2^30 (row index + two flag bits in one word)");
     return SMK_OK;

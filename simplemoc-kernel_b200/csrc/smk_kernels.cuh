@@ -128,12 +128,14 @@ __device__ __forceinline__ float4 ldg4(const float4 *p)
 // ------------------------------------------------------------------------------
 // attenuate_warp_track<GPL, EXPM, F64, GEOM>: one track per warp, GPL groups per lane.
 //
-// Per 32 segments every lane hashes ONE segment of the batch into a packed word
-//     pk = (row * 32) | first | last << 1      row = QSR_id * F + FAI_id, in units of the lane vector
-// (a padded row is 32 lane vectors, so the low 5 bits are free) and sg = QSR_id * 32 for the sigT row.
-// Inside the batch the ids are broadcast with two shuffles; the segment type (first / interior / last fine
-// axial interval) is warp-uniform, so the warp branches into one of three straight-line bodies with literal
-// fit coefficients: each loads only the rows its type reads and the edge bodies skip the quadratic terms.
+// Per 32 segments every lane hashes ONE segment of the batch into two words
+//     pk = row * 32                              row = QSR_id * F + FAI_id, in units of the lane vector
+//     sg = QSR_id * 32 | first << 31 | last << 30   index of the sigT row + the segment type
+// (a padded row is 32 lane vectors, so `| lane` completes either index).  Inside the batch the words are
+// broadcast with two shuffles; the segment type (first / interior / last fine axial interval) is warp-uniform,
+// so the warp branches into one of three straight-line bodies with literal fit coefficients: each loads only
+// the rows its type reads and the edge bodies skip the quadratic terms.  The segment loop is unrolled twice
+// (kSegmentUnroll; +0.7 % at 128 groups, +1.5 % at 64, profiles/ab_r02.md).
 // With GEOM the hashing lane also derives the segment's geometry and fit coefficients and parks them in
 // shared memory; the warp reads them back with broadcast loads.
 // ------------------------------------------------------------------------------
@@ -194,7 +196,11 @@ __device__ __forceinline__ void tally_lane(float *tally, double *tally64, uint32
     }
 }
 
-constexpr uint32_t kPkFirst = 1u, kPkLast = 2u;
+#ifndef SMK_UNROLL_K
+#define SMK_UNROLL_K 2
+#endif
+constexpr int kSegmentUnroll = SMK_UNROLL_K;     // segment loop of attenuate_warp_track (tuning knob)
+constexpr uint32_t kSgFirst = 0x80000000u, kSgLast = 0x40000000u;   // warp_track: type flags above the sigT index
 constexpr uint32_t kRowFirst = 1u << 30, kRowLast = 1u << 31;     // general kernel: flags above the row index
 
 template <int GPL, int EXPM, bool F64, bool GEOM>
@@ -213,7 +219,10 @@ attenuate_warp_track(const KernelArgs a)
         if (threadIdx.x < kTableReach) s_pairs[threadIdx.x] = c_exp_table.pairs[threadIdx.x];
         __syncthreads();
     }
-    const int lane = threadIdx.x & 31;
+    // read once and opaque to the compiler: otherwise every `| lane` is re-derived from threadIdx.x as a
+    // fourth LOP3 input and costs an extra instruction per address
+    int lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
     const int warp = threadIdx.x >> 5;
     const int64_t warp_global = (int64_t)blockIdx.x * kWarps + warp;
     const uint32_t F = (uint32_t)a.fai_count;
@@ -249,8 +258,10 @@ attenuate_warp_track(const KernelArgs a)
                 const uint32_t qsr = fastmod(r.x >> 1, a.mod_regions);       // kernel.c:47
                 const uint32_t fai = fastmod(r.y >> 1, a.mod_fai);           // kernel.c:50
                 checksum += checksum_term(qsr, fai, F, seg);
-                my_pk = ((qsr * F + fai) * ROWV) | (fai == 0u ? kPkFirst : 0u) | (fai == F - 1u ? kPkLast : 0u);
-                my_sg = qsr * ROWV;
+                // type flags in the two top bits of the sigT index (smk_create checks R * 32 < 2^30): `first` is a
+                // sign test, and the row index needs no masking
+                my_pk = (qsr * F + fai) * ROWV;
+                my_sg = (qsr * ROWV) | (fai == 0u ? kSgFirst : 0u) | (fai == F - 1u ? kSgLast : 0u);
                 if constexpr (GEOM) {
                     const SegGeometry g = segment_geometry(a.geom, r.z, r.w);
                     const FitCoeffs f = fit_coeffs_geom_typed(g, a.mesh, fai == 0u || fai == F - 1u);
@@ -260,22 +271,13 @@ attenuate_warp_track(const KernelArgs a)
             }
             if constexpr (GEOM) __syncwarp();
             const int count = (nseg - b) < 32 ? (nseg - b) : 32;
-#ifdef SMK_PF_SIGT
-            // the sigT row heads the dependency chain (tau -> exp): fetch it one segment ahead
-            V st_next = LaneVec<GPL>::load(sigT + (__shfl_sync(kFull, my_sg, 0) | (uint32_t)lane));
-#endif
+#pragma unroll kSegmentUnroll
             for (int k = 0; k < count; ++k) {
                 const uint32_t pk = __shfl_sync(kFull, my_pk, k);
-                const uint32_t idx = (pk & ~31u) | (uint32_t)lane;
+                const uint32_t idx = pk | (uint32_t)lane;
                 const V *src = source + idx;
-#ifdef SMK_PF_SIGT
-                const V st = st_next;
-                const int kn = (k + 1 < count) ? k + 1 : k;
-                st_next = LaneVec<GPL>::load(sigT + (__shfl_sync(kFull, my_sg, kn) | (uint32_t)lane));
-#else
                 const uint32_t sg = __shfl_sync(kFull, my_sg, k);
-                const V st = LaneVec<GPL>::load(sigT + (sg | (uint32_t)lane));
-#endif
+                const V st = LaneVec<GPL>::load(sigT + ((sg & ~(kSgFirst | kSgLast)) | (uint32_t)lane));
                 FitCoeffs fc = {};
                 if constexpr (GEOM) {
                     const float4 c0 = s_coef[warp][k][0], c1 = s_coef[warp][k][1];
@@ -283,11 +285,11 @@ attenuate_warp_track(const KernelArgs a)
                     fc.q1_d = c1.x; fc.q1_s = c1.y; fc.q2_s = c1.z;
                 }
                 V t;
-                if (pk & kPkFirst) {
+                if ((int32_t)sg < 0) {
                     const V y2 = LaneVec<GPL>::load(src);
                     const V y3 = LaneVec<GPL>::load(src + ROWV);
                     attenuate_lane<EXPM, kFitFirst, GEOM>(fc, LaneVec<GPL>::zero(), y2, y3, st, s_pairs, psi, t);
-                } else if (pk & kPkLast) {
+                } else if (sg & kSgLast) {
                     const V y1 = LaneVec<GPL>::load(src - ROWV);
                     const V y2 = LaneVec<GPL>::load(src);
                     attenuate_lane<EXPM, kFitLast, GEOM>(fc, y1, y2, LaneVec<GPL>::zero(), st, s_pairs, psi, t);
