@@ -377,7 +377,8 @@ attenuate_tracks(const KernelArgs a)
         for (int b = 0; b < nseg_warp; b += LPT) {
             // each lane of the track draws the ids of one of the next LPT segments
             // packed: row = QSR_id * F + FAI_id (< 2^29: smk_create checks R * F * G_pad / 4 < 2^31), first / last flags
-            uint32_t my_qsr = 0u, my_row = 0u, my_w2 = 0u, my_w3 = 0u;
+            // lanes without a segment (ragged last track, short batch) keep both flags set: no neighbouring row is read
+            uint32_t my_qsr = 0u, my_row = kRowFirst | kRowLast, my_w2 = 0u, my_w3 = 0u;
             if (b + sub < nseg) {
                 const uint64_t seg = (uint64_t)(s0 + b + sub);
                 const u32x4 w = stream_words(a.keys, seg, 0u, kDomainSegment);
