@@ -524,7 +524,13 @@ def main_ours(a):
     binding, other = main.rooflines(kernel_total_ms / a.steps, clocks, hbm_resident)
     binding["kernel"] = main.ctx.kernel_name
     binding["kernel_ms"] = kernel_total_ms / a.steps
-    binding["traffic"] = recorded_traffic("hbm_resident" if hbm_resident else "config2") if G == 128 else None
+    # measured DRAM bytes of one launch (ncu --set full of this round, profiles/traffic_r02.json).  L2-resident:
+    # the working set is read once per launch whatever the segment count; HBM-resident: valid for 1e8 segments
+    rec = recorded_traffic("hbm_resident" if hbm_resident else "config2") if G == 128 else None
+    if rec and hbm_resident and main.my_segments != 100_000_000:
+        rec = None
+    binding["traffic"] = rec["dram_bytes_per_launch"] if rec else None
+    binding["traffic_source"] = rec["source"] if rec else None
     binding["why"] = ("working set exceeds the L2: DRAM binds" if hbm_resident else
                       "the 38 MB working set is L2-resident (DRAM traffic per launch under `traffic` vs "
                       f"{ALGO_BYTES_PER_INTERSECTION * main.my_segments * G / 1e9:.0f} GB algorithmic): the FP32 pipe binds")
