@@ -498,6 +498,43 @@ def test_cross_sections_above_one(smk, oracle, R, F, G, N, p, seed):
 
 
 # ---------------------------------------------------------------------------------------
+# degenerate cross sections: the values the mini-app's own fill can produce at the small end
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("G", [128, 64, 7])
+def test_zero_and_smallest_cross_sections(smk, oracle, G):
+    """(float) rand() / RAND_MAX (init.c:75) is 0 with probability 2^-31 and otherwise at least 2^-31.  sigT = 0
+    makes the reference divide 0 by 0 (kernel.c:236,249): the NaN stays in that group's angular flux for the
+    rest of the track and lands in every tally it touches.  sigT = 2^-31 is finite in the reference (fluxes
+    up to 1e28).  The GPU has to show the same finite / non-finite pattern and meet
+    the gates on everything finite, in both arithmetic modes."""
+    R, F, N, p, seed = 50, 5, 20_000, 100, 61
+    src, flux0, sig = oracle.fill(R, F, G, seed)
+    sig[3, G // 2] = 0.0
+    sig[10, 1] = sig[20, G - 1] = np.float32(2.0 ** -31)
+    sig[30, 0] = np.float32(3 * 2.0 ** -31)
+    want = flux0.copy()
+    psi_want, chk_want = oracle.run(src, want, sig, N, p, seed, want_psi=True, nthreads=1)
+    bad = ~np.isfinite(want)
+    assert bad.any() and not bad.all() and np.abs(want[~bad]).max() > 1e20
+
+    I = make_input(smk, R, F, G, N, p, seed, "glibc", "strict")
+    flux, psi, chk = gpu_run(smk, I, src, flux0, sig, keep_psi=True)
+    assert chk == chk_want
+    assert np.array_equal(np.isnan(psi), np.isnan(psi_want))
+    ok = ~np.isnan(psi_want)
+    assert np.array_equal(bits(psi[ok]), bits(psi_want[ok]))
+    assert np.array_equal(np.isfinite(flux), ~bad)
+    assert l2rel(flux[~bad], want[~bad]) <= TOL_STRICT
+
+    for exp_mode in ("poly", "glibc"):
+        I = make_input(smk, R, F, G, N, p, seed, exp_mode, "fast")
+        flux, _, chk = gpu_run(smk, I, src, flux0, sig)
+        assert chk == chk_want
+        assert np.array_equal(np.isfinite(flux), ~bad), exp_mode
+        assert l2rel(flux[~bad], want[~bad]) <= TOL_FAST, exp_mode
+
+
+# ---------------------------------------------------------------------------------------
 # per-segment geometry (SMK_FLAG_SEGMENT_GEOMETRY; kernel.c:95-104; SURVEY.md section 8(f) rank 4)
 # ---------------------------------------------------------------------------------------
 GEOM_BASE = (0.2, 0.05, 0.8, 0.6, 0.36, 0.45)      # a non-reference geometry with mu2 = mu^2
