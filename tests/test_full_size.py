@@ -142,3 +142,29 @@ def test_full_size_flux_parity(smk, oracle, name, r2d, groups, segments, deep):
                 ctx.run()
                 got32 = ctx.download_flux()
             assert l2rel(got32, got) <= 1e-4
+
+
+def test_full_size_per_segment_geometry_parity(smk, oracle):
+    """BASELINE config 2 (128 groups, 1e8 segments) with per-segment geometry (kernel.c:95-104 as stream-driven
+    parameters, spread 0.25: ds reaches 0.875, so POLY runs in its wide-range form) against a FULL CPU replay of
+    the parametrised oracle: same gates as the constant geometry."""
+    from oracle.oracle import GEOM, REFERENCE_GEOMETRY, geometry7
+    I = smk.Input(source_2D_regions=5000, segments=100_000_000, egroups=128, seed=SEED,
+                  segment_geometry=True, geometry_spread=0.25).finalize()
+    Rr, Fr = I.source_3D_regions, I.fine_axial_intervals
+    src, flux0, sig = oracle.fill(Rr, Fr, 128, SEED)
+    want = flux0.copy()
+    _, chk_want = oracle.run(src, want, sig, I.segments, I.seg_per_thread, SEED, nthreads=0, flags=GEOM,
+                             geom7=geometry7(REFERENCE_GEOMETRY, 0.25))
+    for math_mode, exp_mode, tol in (("fast", "poly", 1e-5), ("strict", "glibc", 5e-6)):
+        I.math_mode, I.exp_mode = math_mode, exp_mode
+        with smk.Context(I) as ctx:
+            ctx.upload(src, flux0, sig)
+            assert "per-segment" in ctx.kernel_name
+            ctx.run()
+            got, chk = ctx.download_flux(), ctx.checksum()
+        assert chk == chk_want
+        assert np.array_equal(np.isfinite(got), np.isfinite(want))
+        err = l2rel(got, want)
+        print(f"config 2 + per-segment geometry {math_mode}/{exp_mode}: L2-rel {err:.3e}")
+        assert err <= tol, f"{math_mode}/{exp_mode}: {err:.3e}"
