@@ -141,31 +141,34 @@ static AttenuateFn pick_general(const Shape &s, int math, int expm)
 }
 
 // one track per warp, FAST arithmetic: 4 groups per lane (65..128 groups) or 2 (33..64)
-template <int GPL, bool F64, bool GEOM>
+template <int GPL, bool F64, bool GEOM, bool A32>
 static AttenuateFn pick_warp_track_exp(int expm)
 {
     switch (expm) {
-        case kExpPoly: return attenuate_warp_track<GPL, kExpPoly, F64, GEOM>;
-        case kExpPolyWide: return attenuate_warp_track<GPL, kExpPolyWide, F64, GEOM>;
-        case kExpMufu: return attenuate_warp_track<GPL, kExpMufu, F64, GEOM>;
-        case kExpGlibc: return attenuate_warp_track<GPL, kExpGlibc, F64, GEOM>;
-        case kExpTable: return attenuate_warp_track<GPL, kExpTable, F64, GEOM>;
+        case kExpPoly: return attenuate_warp_track<GPL, kExpPoly, F64, GEOM, A32>;
+        case kExpPolyWide: return attenuate_warp_track<GPL, kExpPolyWide, F64, GEOM, A32>;
+        case kExpMufu: return attenuate_warp_track<GPL, kExpMufu, F64, GEOM, A32>;
+        case kExpGlibc: return attenuate_warp_track<GPL, kExpGlibc, F64, GEOM, A32>;
+        case kExpTable: return attenuate_warp_track<GPL, kExpTable, F64, GEOM, A32>;
     }
     return nullptr;
 }
 
+// a32: every array < 4 GB -> 32-bit byte offsets (only the f32-tally kernels have that form: the f64 tallies are a
+// diagnostic)
 template <int GPL>
-static AttenuateFn pick_warp_track(int expm, bool f64, bool geom)
+static AttenuateFn pick_warp_track(int expm, bool f64, bool geom, bool a32)
 {
-    if (f64) return geom ? pick_warp_track_exp<GPL, true, true>(expm) : pick_warp_track_exp<GPL, true, false>(expm);
-    return geom ? pick_warp_track_exp<GPL, false, true>(expm) : pick_warp_track_exp<GPL, false, false>(expm);
+    if (f64) return geom ? pick_warp_track_exp<GPL, true, true, false>(expm) : pick_warp_track_exp<GPL, true, false, false>(expm);
+    if (a32) return geom ? pick_warp_track_exp<GPL, false, true, true>(expm) : pick_warp_track_exp<GPL, false, false, true>(expm);
+    return geom ? pick_warp_track_exp<GPL, false, true, false>(expm) : pick_warp_track_exp<GPL, false, false, false>(expm);
 }
 
 // expm is the internal mode (kExpPolyWide resolved by the caller)
-static KernelChoice choose_kernel(const Shape &s, int math, int expm, bool f64, bool geom)
+static KernelChoice choose_kernel(const Shape &s, int math, int expm, bool f64, bool geom, bool a32)
 {
-    if (math == kMathFast && s.nchunk == 1 && s.lpt == 32) return {pick_warp_track<4>(expm, f64, geom), "attenuate_warp_track<4 groups/lane"};
-    if (math == kMathFast && s.nchunk == 1 && s.lpt == 16) return {pick_warp_track<2>(expm, f64, geom), "attenuate_warp_track<2 groups/lane"};
+    if (math == kMathFast && s.nchunk == 1 && s.lpt == 32) return {pick_warp_track<4>(expm, f64, geom, a32), "attenuate_warp_track<4 groups/lane"};
+    if (math == kMathFast && s.nchunk == 1 && s.lpt == 16) return {pick_warp_track<2>(expm, f64, geom, a32), "attenuate_warp_track<2 groups/lane"};
     return {geom ? pick_general<true>(s, math, expm) : pick_general<false>(s, math, expm), "attenuate_tracks<general"};
 }
 
@@ -288,8 +291,14 @@ static int select_kernel(smk_ctx *c)
     }
     AttenuateFn fn = c->tuning_kernel;
     const char *family = "tuning variant";
+    // 32-bit byte offsets reach every element when the largest array (R * F padded rows) is below 4 GB
+    // (SMK_ADDR64=1 forces the plain form: tests of the > 4 GB path on small data)
+    const char *force64 = getenv("SMK_ADDR64");
+    const bool a32 = (uint64_t)c->rows * c->shape.groups_pad * sizeof(float) < (1ull << 32) && !(force64 && force64[0] == '1');
+    bool warp_track32 = false;
     if (!fn) {
-        const KernelChoice k = choose_kernel(c->shape, c->p.math_mode, expm, f64, geom);
+        const KernelChoice k = choose_kernel(c->shape, c->p.math_mode, expm, f64, geom, a32);
+        warp_track32 = a32 && !f64 && strncmp(k.family, "attenuate_warp_track", 20) == 0;
         fn = k.fn;
         family = k.family;
     }
@@ -302,9 +311,9 @@ static int select_kernel(smk_ctx *c)
         if (c->blocks_per_sm < 1) c->blocks_per_sm = 1;
     }
     c->exp_internal = expm;
-    snprintf(c->kernel_name, sizeof c->kernel_name, "%s, %s, %s, %s tally, %s geometry>", family,
+    snprintf(c->kernel_name, sizeof c->kernel_name, "%s, %s, %s, %s tally, %s geometry%s>", family,
              c->p.math_mode == kMathStrict ? "strict" : "fast", exp_name[expm], f64 ? "f64" : "f32",
-             geom ? "per-segment" : "const");
+             geom ? "per-segment" : "const", warp_track32 ? ", 32-bit offsets" : "");
     return SMK_OK;
 }
 

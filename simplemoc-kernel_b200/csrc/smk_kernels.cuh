@@ -1,6 +1,6 @@
 // smk_kernels.cuh -- sm_100a kernels of the segment-attenuation path.
 //
-//   attenuate_warp_track<GPL, EXPM, F64, GEOM>    the hot kernels: run_kernel's segment loop +
+//   attenuate_warp_track<GPL, EXPM, F64, GEOM, A32> the hot kernels: run_kernel's segment loop +
 //       attenuate_segment (/root/reference/src/cpu/kernel.c:43-55, 75-333), ONE WARP PER TRACK, FAST
 //       arithmetic.  GPL = energy groups per lane: 4 for 65..128 groups (128-bit loads, red.v4), 2 for
 //       33..64 groups (64-bit loads, red.v2).
@@ -126,7 +126,8 @@ __device__ __forceinline__ float4 ldg4(const float4 *p)
 }
 
 // ------------------------------------------------------------------------------
-// attenuate_warp_track<GPL, EXPM, F64, GEOM>: one track per warp, GPL groups per lane.
+// attenuate_warp_track<GPL, EXPM, F64, GEOM, A32>: one track per warp, GPL groups per lane; A32 = every array is
+// smaller than 4 GB, addresses from 32-bit byte offsets (ptr_add_index).
 //
 // Per 32 segments every lane hashes ONE segment of the batch into two words
 //     pk = row * 32                              row = QSR_id * F + FAI_id, in units of the lane vector
@@ -139,6 +140,30 @@ __device__ __forceinline__ float4 ldg4(const float4 *p)
 // With GEOM the hashing lane also derives the segment's geometry and fit coefficients and parks them in
 // shared memory; the warp reads them back with broadcast loads.
 // ------------------------------------------------------------------------------
+// base + idx * sizeof(T) for a 32-bit element index.  Left to itself ptxas emits IMAD.WIDE.U32 for every such
+// address (and turns a hand-written shift / add-with-carry sequence back into one), and IMAD runs on the FMA-heavy
+// pipe -- the unit that binds the FAST kernels (82 % busy, profiles/ncu_r02_default.md).  With A32 the BYTE offset is
+// formed in 32-bit arithmetic and added with an explicit add / add-with-carry pair, which ptxas keeps on the integer
+// ALU (SASS: LEA + IADD3.X from a uniform-register base): +3 % at 128 groups, +6 % at 64 (profiles/ab_r02.md).
+// Bits of idx that the 32-bit product shifts out (the type flags of `sg`) vanish for free.  The library selects
+// A32 when every array is smaller than 4 GB (all BASELINE configurations and the 4.6 GB HBM-resident set, whose
+// largest array is 1.5 GB), the plain form otherwise.
+template <bool A32, typename T>
+__device__ __forceinline__ T *ptr_add_index(T *base, uint32_t idx)
+{
+    if constexpr (A32) {
+        const uint64_t b = reinterpret_cast<uint64_t>(base);
+        const uint32_t bytes = idx * (uint32_t)sizeof(T);
+        uint32_t lo, hi;
+        asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, 0;"
+            : "=r"(lo), "=r"(hi)
+            : "r"((uint32_t)b), "r"((uint32_t)(b >> 32)), "r"(bytes));
+        return reinterpret_cast<T *>(((uint64_t)hi << 32) | lo);
+    } else {
+        return base + idx;
+    }
+}
+
 template <int GPL>
 struct LaneVec;
 template <>
@@ -175,24 +200,24 @@ __device__ __forceinline__ void attenuate_lane(const FitCoeffs &fc, float2 y1, f
 }
 
 // FSR_flux[g] += tally[g] (kernel.c:276): one vector RED per lane, or f64 REDs for the diagnostic tallies
-template <bool F64>
+template <bool F64, bool A32>
 __device__ __forceinline__ void tally_lane(float *tally, double *tally64, uint32_t idx, const float4 &t)
 {
     if constexpr (F64) {
         double *d = tally64 + (size_t)idx * 4;
         red_add_f64(d, t.x); red_add_f64(d + 1, t.y); red_add_f64(d + 2, t.z); red_add_f64(d + 3, t.w);
     } else {
-        red_add_v4(reinterpret_cast<float4 *>(tally) + idx, t.x, t.y, t.z, t.w);
+        red_add_v4(ptr_add_index<A32>(reinterpret_cast<float4 *>(tally), idx), t.x, t.y, t.z, t.w);
     }
 }
-template <bool F64>
+template <bool F64, bool A32>
 __device__ __forceinline__ void tally_lane(float *tally, double *tally64, uint32_t idx, const float2 &t)
 {
     if constexpr (F64) {
         double *d = tally64 + (size_t)idx * 2;
         red_add_f64(d, t.x); red_add_f64(d + 1, t.y);
     } else {
-        red_add_v2(reinterpret_cast<float2 *>(tally) + idx, t.x, t.y);
+        red_add_v2(ptr_add_index<A32>(reinterpret_cast<float2 *>(tally), idx), t.x, t.y);
     }
 }
 
@@ -203,7 +228,7 @@ constexpr int kSegmentUnroll = SMK_UNROLL_K;     // segment loop of attenuate_wa
 constexpr uint32_t kSgFirst = 0x80000000u, kSgLast = 0x40000000u;   // warp_track: type flags above the sigT index
 constexpr uint32_t kRowFirst = 1u << 30, kRowLast = 1u << 31;     // general kernel: flags above the row index
 
-template <int GPL, int EXPM, bool F64, bool GEOM>
+template <int GPL, int EXPM, bool F64, bool GEOM, bool A32>
 __global__ void __launch_bounds__(kThreadsPerBlock, GEOM ? kMinBlocksGeom : kMinBlocksFast)
 attenuate_warp_track(const KernelArgs a)
 {
@@ -275,9 +300,9 @@ attenuate_warp_track(const KernelArgs a)
             for (int k = 0; k < count; ++k) {
                 const uint32_t pk = __shfl_sync(kFull, my_pk, k);
                 const uint32_t idx = pk | (uint32_t)lane;
-                const V *src = source + idx;
                 const uint32_t sg = __shfl_sync(kFull, my_sg, k);
-                const V st = LaneVec<GPL>::load(sigT + ((sg & ~(kSgFirst | kSgLast)) | (uint32_t)lane));
+                const V *src = ptr_add_index<A32>(source, idx);
+                const V st = LaneVec<GPL>::load(ptr_add_index<A32>(sigT, (sg & ~(kSgFirst | kSgLast)) | (uint32_t)lane));
                 FitCoeffs fc = {};
                 if constexpr (GEOM) {
                     const float4 c0 = s_coef[warp][k][0], c1 = s_coef[warp][k][1];
@@ -299,7 +324,7 @@ attenuate_warp_track(const KernelArgs a)
                     const V y3 = LaneVec<GPL>::load(src + ROWV);
                     attenuate_lane<EXPM, kFitInterior, GEOM>(fc, y1, y2, y3, st, s_pairs, psi, t);
                 }
-                tally_lane<F64>(tally, a.tally64, idx, t);                             // kernel.c:276
+                tally_lane<F64, A32>(tally, a.tally64, idx, t);                             // kernel.c:276
             }
             if constexpr (GEOM) __syncwarp();       // everyone is done with s_coef before the next batch overwrites it
         }

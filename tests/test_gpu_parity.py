@@ -498,6 +498,35 @@ def test_cross_sections_above_one(smk, oracle, R, F, G, N, p, seed):
 
 
 # ---------------------------------------------------------------------------------------
+# address forms of the one-track-per-warp kernels
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("G,geom", [(128, False), (64, False), (128, True)])
+def test_wide_and_32bit_address_forms_agree(smk, oracle, monkeypatch, G, geom):
+    """Arrays below 4 GB are addressed with 32-bit byte offsets (integer-ALU address arithmetic instead of
+    IMAD.WIDE on the FMA-heavy pipe); larger ones with the plain 64-bit form, forced here on small data with
+    SMK_ADDR64=1.  Same arithmetic: STRICT-free FAST psi per track must agree bit for bit between the two."""
+    R, F, N, p, seed = 120, 5, 60_000, 100, 71
+    src, flux0, sig = oracle.fill(R, F, G, seed)
+    want = flux0.copy()
+    g = (REFERENCE_GEOMETRY, 0.25) if geom else None
+    _, chk_want = oracle.run(src, want, sig, N, p, seed, nthreads=0, flags=GEOM if geom else 0,
+                             geom7=geometry7(REFERENCE_GEOMETRY, 0.25) if geom else None)
+    out = {}
+    for force in ("0", "1"):
+        monkeypatch.setenv("SMK_ADDR64", force)
+        I = make_input(smk, R, F, G, N, p, seed, "poly", "fast", geom=g)
+        with smk.Context(I, keep_psi=True) as ctx:
+            ctx.upload(src, flux0, sig)
+            name = ctx.kernel_name
+            ctx.run()
+            out[force] = (ctx.download_flux(), ctx.download_psi(ctx.n_tracks), ctx.checksum())
+        assert ("32-bit offsets" in name) == (force == "0"), name
+        assert out[force][2] == chk_want
+        assert l2rel(out[force][0], want) <= TOL_FAST
+    assert np.array_equal(bits(out["0"][1]), bits(out["1"][1]))
+
+
+# ---------------------------------------------------------------------------------------
 # degenerate cross sections: the values the mini-app's own fill can produce at the small end
 # ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("G", [128, 64, 7])
