@@ -366,28 +366,35 @@ __device__ __forceinline__ void attenuate_fast2(const FitCoeffs &f, float2 y1, f
     // (1 - tau) comes rounded from the exponential: 6e-8 absolute on a sum that is >= 0.5 (2 expVal / sigT^3
     // >= 2 ds / sigT^2 - ..., while tau (tau - 2) >= -1), one operation instead of two.
     const float2 reuse = fma2(f2(2.0f), mul2(E, rs2), fma2(omt, omt, f2(-1.0f)));
-    float2 fi = fma2(Q1, reuse, fma2(q0, Fc, mul2(psi, E)));
+    // The flux integral (kernel.c:248-251) and the outgoing flux (kernel.c:291-331) are both sums of four products
+    // over (psi, mu2 q2, mu q1, q0).  They advance in lock step, largest-index term first, so that the two FMAs of
+    // a step share their first operand: ptxas schedules them back to back with the operand held in the reuse
+    // cache, and a three-register FFMA2 then costs 2 issue cycles instead of 3 (tools/ubench/fp2_operands.cu).
+    float2 fi = mul2(psi, E);                                        // sigT psi expVal / sigT^2
     float2 acc = mul2(psi, e);                                       // t4 = psi (1 - expVal), kernel.c:321
     if constexpr (kQuadratic) {
-        // tau (tau (tau - 3) + 6) - 6 expVal, kernel.c:250, in the reference's order of operations: its true
-        // value is ~tau^4/4 while its terms are ~6 tau, so for small sigT it is pure rounding noise
-        // (cancellation factor 24/tau^3) that, divided by 3 sigT^4, reaches 1e-4 of the dominant term, and
-        // parity needs the reference's own roundings of the two large terms: 6 expVal is rounded before the
-        // subtraction (sub2 = fma(b, -1, a) adds nothing to that).  Measured (gpurun r01a, reproduced by
-        // CPU emulation): with the subtraction contracted into fma(-6, expVal, ...) 1.2e-4 L2-relative,
-        // this form 3.6e-8.  (ptxas does fuse tau (tau - 3) + 6 into one FFMA2; that rounding is below the
-        // noise floor of the term.)
+        // tau (tau (tau - 3) + 6) - 6 expVal, kernel.c:250, in the reference's order of operations: its true value is
+        // ~tau^4/4 while its terms are ~6 tau, so for small sigT it is pure rounding noise (cancellation factor
+        // 24/tau^3) that, divided by 3 sigT^4, reaches 1e-4 of the dominant term, and parity needs the reference's own
+        // roundings of the two large terms: 6 expVal is rounded before the subtraction (sub2 = fma(b, -1, a) adds
+        // nothing to that).  Measured (gpurun r01a, reproduced by CPU emulation): with the subtraction contracted into
+        // fma(-6, expVal, ...) 1.2e-4 L2-relative, this form 3.6e-8.  (ptxas does fuse tau (tau - 3) + 6 into one
+        // FFMA2; that rounding is below the noise floor of the term.)
         const float2 cubic = sub2(mul2(tau, add2(mul2(tau, add2(tau, f2(-3.0f))), f2(6.0f))),
                                   mul2(f2(6.0f), ev));
-        fi = fma2(mul2(Q2, f2(1.0f / 3.0f)), mul2(cubic, mul2(rs2, rs2)), fi);         // kernel.c:250-251
+        const float2 h3 = mul2(mul2(cubic, mul2(rs2, rs2)), f2(1.0f / 3.0f));           // cubic / (3 sigT^4)
+        fi = fma2(Q2, h3, fi);                                                          // kernel.c:250-251
         acc = fma2(Q2, reuse, acc);                                                     // t3, kernel.c:311
     }
+    fi = fma2(Q1, reuse, fi);                                        // term2, kernel.c:249
+    acc = fma2(Q1, Fc, acc);                                         // t2, kernel.c:301
+    fi = fma2(q0, Fc, fi);                                           // term1: q0 (tau - expVal) / sigT^2
     // kernel.c:262.  With the constant geometry the weight is the same for every segment and is applied once
     // to the summed tallies by finalize_flux (kTallyScaleConst; 0.5 is a power of two, so the result is
     // bit-identical to weighting every contribution); per-segment weights are applied here.
     if constexpr (GEOM) tally = mul2(f2(f.weight), fi);
     else tally = fi;
-    psi = fma2(q0, E, fma2(Q1, Fc, acc));                            // kernel.c:331
+    psi = fma2(q0, E, acc);                                          // t1, kernel.c:291; sum kernel.c:331
 }
 
 // STRICT: one intersection in the reference's own operation order; g holds kernel.c:99-104

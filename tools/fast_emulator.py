@@ -101,20 +101,34 @@ def attenuate_fast(kind, fc, y1, y2, y3, sigT, psi, variant="cur"):
     else:
         # tau^2 - 2 tau = (1 - tau)^2 - 1 from the exponential's s = RN(1 - tau): one operation
         reuse = fma(f32(2.0), mul(E, rs2), fma(one_m_tau, one_m_tau, f32(-1.0)))
-    fi = fma(Q1, reuse, fma(q0, Fc, mul(psi, E)))
-    acc = mul(psi, e)
-    if variant in ("cur", "old_reuse"):
-        cubic = sub(mul(tau, fma(tau, add(tau, f32(-3.0)), f32(6.0))), mul(f32(6.0), ev))   # as ptxas fuses it
-    elif variant == "nofuse":
-        cubic = sub(mul(tau, add(mul(tau, add(tau, f32(-3.0))), f32(6.0))), mul(f32(6.0), ev))
+    if variant == "chain_r02f":
+        # accumulation order of the kernels up to gpurun r02h
+        fi = fma(Q1, reuse, fma(q0, Fc, mul(psi, E)))
+        acc = mul(psi, e)
+        cubic = sub(mul(tau, fma(tau, add(tau, f32(-3.0)), f32(6.0))), mul(f32(6.0), ev))
+        fi_q = fma(mul(Q2, f32(1.0 / 3.0)), mul(cubic, mul(rs2, rs2)), fi)
+        acc_q = fma(Q2, reuse, acc)
+        fi = np.where(interior, fi_q, fi)
+        acc = np.where(interior, acc_q, acc)
+        psi_new = fma(q0, E, fma(Q1, Fc, acc))
     else:
-        raise ValueError(variant)
-    fi_q = fma(mul(Q2, f32(1.0 / 3.0)), mul(cubic, mul(rs2, rs2)), fi)
-    acc_q = fma(Q2, reuse, acc)
-    fi = np.where(interior, fi_q, fi)
-    acc = np.where(interior, acc_q, acc)
+        # the two sums advance in lock step, each pair of FMAs sharing its first operand (psi, Q2, Q1, q0)
+        fi = mul(psi, E)
+        acc = mul(psi, e)
+        if variant in ("cur", "old_reuse"):
+            cubic = sub(mul(tau, fma(tau, add(tau, f32(-3.0)), f32(6.0))), mul(f32(6.0), ev))   # as ptxas fuses it
+        elif variant == "nofuse":
+            cubic = sub(mul(tau, add(mul(tau, add(tau, f32(-3.0))), f32(6.0))), mul(f32(6.0), ev))
+        else:
+            raise ValueError(variant)
+        h3 = mul(mul(cubic, mul(rs2, rs2)), f32(1.0 / 3.0))
+        fi = np.where(interior, fma(Q2, h3, fi), fi)
+        acc = np.where(interior, fma(Q2, reuse, acc), acc)
+        fi = fma(Q1, reuse, fi)
+        acc = fma(Q1, Fc, acc)
+        fi = fma(q0, Fc, fi)
+        psi_new = fma(q0, E, acc)
     tally = mul(fc["weight"], fi)
-    psi_new = fma(q0, E, fma(Q1, Fc, acc))
     return psi_new, tally
 
 
