@@ -228,8 +228,14 @@ constexpr int kSegmentUnroll = SMK_UNROLL_K;     // segment loop of attenuate_wa
 constexpr uint32_t kSgFirst = 0x80000000u, kSgLast = 0x40000000u;   // warp_track: type flags above the sigT index
 constexpr uint32_t kRowFirst = 1u << 30, kRowLast = 1u << 31;     // general kernel: flags above the row index
 
+#ifndef SMK_MIN_BLOCKS_HALF
+#define SMK_MIN_BLOCKS_HALF SMK_MIN_BLOCKS_FAST
+#endif
+// two groups per lane need fewer registers (46): more resident warps make up for the single dependency chain per lane
+constexpr int kMinBlocksHalf = SMK_MIN_BLOCKS_HALF;
+
 template <int GPL, int EXPM, bool F64, bool GEOM, bool A32>
-__global__ void __launch_bounds__(kThreadsPerBlock, GEOM ? kMinBlocksGeom : kMinBlocksFast)
+__global__ void __launch_bounds__(kThreadsPerBlock, GEOM ? kMinBlocksGeom : (GPL == 2 ? kMinBlocksHalf : kMinBlocksFast))
 attenuate_warp_track(const KernelArgs a)
 {
     typedef typename LaneVec<GPL>::type V;
