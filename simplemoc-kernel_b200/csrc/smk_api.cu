@@ -97,6 +97,11 @@ static bool shape_for(int groups, Shape &s)
 
 typedef void (*AttenuateFn)(const KernelArgs);
 
+// groups per lane of attenuate_record_tracks: four (two 256-bit loads per lane and segment) from 5 groups up, two for
+// 1..4 groups, where four would leave one lane per track (measured, profiles/ab_r02.md: 29 groups 5.63e11 vs 5.42e11,
+// 13 groups 4.62e11 vs 4.49e11, 7 groups equal, 3 groups 2.25e11 vs 2.80e11)
+static int record_groups_per_lane(int groups_pad) { return groups_pad >= 8 ? 4 : 2; }
+
 struct KernelChoice {
     AttenuateFn fn;
     const char *family;
@@ -164,6 +169,31 @@ static AttenuateFn pick_warp_track(int expm, bool f64, bool geom, bool a32)
     return geom ? pick_warp_track_exp<GPL, false, true, false>(expm) : pick_warp_track_exp<GPL, false, false, false>(expm);
 }
 
+// sub-warp tracks from gather records (<= 32 groups, FAST, constant geometry); lpt = lanes per track = G_pad / gpl
+template <int LPT, int GPL, bool F64>
+static AttenuateFn pick_record_exp(int expm)
+{
+    switch (expm) {
+        case kExpPoly: return attenuate_record_tracks<LPT, GPL, kExpPoly, F64>;
+        case kExpPolyWide: return attenuate_record_tracks<LPT, GPL, kExpPolyWide, F64>;
+        case kExpMufu: return attenuate_record_tracks<LPT, GPL, kExpMufu, F64>;
+        case kExpGlibc: return attenuate_record_tracks<LPT, GPL, kExpGlibc, F64>;
+        case kExpTable: return attenuate_record_tracks<LPT, GPL, kExpTable, F64>;
+    }
+    return nullptr;
+}
+
+template <int GPL>
+static AttenuateFn pick_record(int groups_pad, int expm, bool f64)
+{
+    switch (groups_pad / GPL) {
+#define SMK_PICK(L) case L: return f64 ? pick_record_exp<L, GPL, true>(expm) : pick_record_exp<L, GPL, false>(expm);
+        SMK_PICK(1) SMK_PICK(2) SMK_PICK(4) SMK_PICK(8) SMK_PICK(16)
+#undef SMK_PICK
+    }
+    return nullptr;
+}
+
 // expm is the internal mode (kExpPolyWide resolved by the caller)
 static KernelChoice choose_kernel(const Shape &s, int math, int expm, bool f64, bool geom, bool a32)
 {
@@ -203,6 +233,8 @@ struct smk_ctx {
     unsigned long long *d_work;  // dynamic track scheduling counter
     unsigned int *d_max_bits;    // smk_scan_sigt_max scratch
     double *d_tally64;           // SMK_FLAG_TALLY_F64: f64 tally accumulators, [R][F][G_pad]
+    float *d_records;            // gather records of attenuate_record_tracks, [R*F][G_pad/2][8]; nullptr = not used
+    int rec_gpl;                 // groups per lane of the record kernel (2 or 4)
     float sigt_max;              // max(sigT) of the device data, +inf when unknown (partial uploads)
     cudaStream_t stream;
     bool own_stream;
@@ -296,6 +328,10 @@ static int select_kernel(smk_ctx *c)
     const char *force64 = getenv("SMK_ADDR64");
     const bool a32 = (uint64_t)c->rows * c->shape.groups_pad * sizeof(float) < (1ull << 32) && !(force64 && force64[0] == '1');
     bool warp_track32 = false;
+    if (!fn && c->d_records) {
+        fn = c->rec_gpl == 2 ? pick_record<2>(c->shape.groups_pad, expm, f64) : pick_record<4>(c->shape.groups_pad, expm, f64);
+        family = c->rec_gpl == 2 ? "attenuate_record_tracks<2 groups/lane" : "attenuate_record_tracks<4 groups/lane";
+    }
     if (!fn) {
         const KernelChoice k = choose_kernel(c->shape, c->p.math_mode, expm, f64, geom, a32);
         warp_track32 = a32 && !f64 && strncmp(k.family, "attenuate_warp_track", 20) == 0;
@@ -414,6 +450,20 @@ int smk_create(const smk_params *p, smk_ctx **out)
         e = cudaMalloc(&c->d_tally64, 2 * slab);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tally64, 0, 2 * slab, c->stream);
     }
+    // <= 32 groups, FAST, constant geometry: the sweep reads gather records (attenuate_record_tracks), 4 x the
+    // source array, rebuilt from the canonical rows at every launch.  SMK_RECORDS=0 keeps the general kernel
+    // (A/B and the cross-check test), =2 / =4 selects the groups per lane.
+    {
+        int gpl = record_groups_per_lane(shape.groups_pad);
+        if (const char *r = getenv("SMK_RECORDS")) gpl = atoi(r);
+        const bool eligible = shape.nchunk == 1 && shape.groups_pad <= 32 && p->math_mode == kMathFast &&
+                              !(p->flags & SMK_FLAG_SEGMENT_GEOMETRY) && slab * 4 < (1ull << 32) &&
+                              c->rows * (shape.groups_pad / 2) < (1ll << 30);
+        if (eligible && (gpl == 2 || gpl == 4)) {
+            c->rec_gpl = gpl;
+            if (e == cudaSuccess) e = cudaMalloc(&c->d_records, slab * 4);
+        }
+    }
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tally, 0, slab * c->replicas, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_flux0, 0, slab, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_checksum, 0, sizeof(unsigned long long), c->stream);
@@ -453,6 +503,7 @@ void smk_destroy(smk_ctx *c)
     cudaFree(c->d_work);
     cudaFree(c->d_max_bits);
     cudaFree(c->d_tally64);
+    cudaFree(c->d_records);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -687,8 +738,23 @@ static int launch(smk_ctx *c, int64_t track_begin, int64_t track_end)
     const double dz = (double)c->geom.dz;
     a.mesh = MeshConsts{(float)(1.0 / (2.0 * dz)), (float)(1.0 / (2.0 * dz * dz)), (float)(1.0 / dz)};
 
+    a.records = c->d_records;
+    int lanes_per_track = c->shape.lpt;
+    if (c->d_records && !c->tuning_kernel) {
+        // derived layout, rebuilt from the canonical rows inside every sweep (they may have been written through
+        // any of the upload paths or directly on the device since the last one)
+        const int Gp = c->shape.groups_pad;
+        if (c->rec_gpl == 2)
+            build_records<2><<<layout_grid(c->rows * (Gp / 2)), 256, 0, c->stream>>>(c->d_source, c->d_sigT, c->d_records, c->rows, c->p.fine_axial_intervals, Gp);
+        else
+            build_records<4><<<layout_grid(c->rows * (Gp / 4)), 256, 0, c->stream>>>(c->d_source, c->d_sigT, c->d_records, c->rows, c->p.fine_axial_intervals, Gp);
+        SMK_CUDA(cudaGetLastError());
+        c->launches += 1;
+        lanes_per_track = Gp / c->rec_gpl;
+    }
+
     // persistent grid: a whole number of CTAs per SM; warps claim work items dynamically
-    const int slots_per_block = (kThreadsPerBlock / 32) * (32 / c->shape.lpt);
+    const int slots_per_block = (kThreadsPerBlock / 32) * (32 / lanes_per_track);
     const int64_t work = tracks * c->shape.group_blocks;
     int64_t want = (work + slots_per_block - 1) / slots_per_block;
     int64_t full = (int64_t)c->sm_count * c->blocks_per_sm;

@@ -4,6 +4,8 @@
 //       attenuate_segment (/root/reference/src/cpu/kernel.c:43-55, 75-333), ONE WARP PER TRACK, FAST
 //       arithmetic.  GPL = energy groups per lane: 4 for 65..128 groups (128-bit loads, red.v4), 2 for
 //       33..64 groups (64-bit loads, red.v2).
+//   attenuate_record_tracks<LPT, GPL, EXPM, F64> <= 32 groups, FAST, constant geometry: sub-warp tracks fed by one
+//       256-bit load per lane and segment from gather records (build_records)
 //   attenuate_tracks<LPT, NCHUNK, MATH, EXPM, GEOM> the general kernel: sub-warp tracks for <= 32 groups,
 //       blocks of 256 groups for > 128 groups (any group count), and the STRICT verification arithmetic
 //   fill_rows                                    device-side deterministic fill
@@ -54,6 +56,7 @@ struct KernelArgs {
                                          // each (track, block) is swept by its own warp (groups are independent)
     GeometryBase geom;                   // SMK_FLAG_SEGMENT_GEOMETRY: base values + spread (kernel.c:99-104)
     MeshConsts mesh;                     // 1/(2dz), 1/(2dz^2), 1/dz
+    const float *__restrict__ records;   // attenuate_record_tracks: gather records [R*F][G_pad/2][8] (build_records)
 };
 
 #ifndef SMK_THREADS_PER_BLOCK
@@ -481,6 +484,202 @@ attenuate_tracks(const KernelArgs a)
     }
 
     // one 64-bit atomic per warp for the indexing fingerprint
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) checksum += __shfl_xor_sync(kFull, checksum, off);
+    if (lane == 0 && checksum != 0ull) atomicAdd(a.checksum, checksum);
+}
+
+// ------------------------------------------------------------------------------
+// attenuate_record_tracks<LPT, GPL, EXPM, F64>: sub-warp tracks (G_pad <= 32), FAST arithmetic, constant
+// geometry, fed from GATHER RECORDS instead of the row arrays.
+//
+// With few groups a track is a handful of lanes and every lane group gathers its own rows: each of the 3.6 row
+// loads + 1 RED per (track, segment) is its own L1 wavefront (one 32-byte sector per lane pair), and at 7 groups
+// the general kernel sits against the L1 wavefront rate (L1/TEX 89 % busy, profiles/ncu_r02_g7.md) with the
+// FMA pipe half idle.  build_records lays everything one (segment, pair of groups) reads side by side,
+//     rec[row = QSR * F + FAI][j] = { sigT[QSR][2j..2j+1], y[FAI-1][2j..2j+1], y[FAI][2j..2j+1], y[FAI+1][2j..2j+1] }
+// (32 bytes; the missing neighbour of an edge interval is 0, exactly what the general kernel substitutes), so a lane
+// fetches its segment with ONE 256-bit load (SASS LDG.E.256) and the lanes of a track read one contiguous
+// 16 * G_pad-byte record row (one 128-byte line at 7 groups): 1 load wavefront per (track, segment) instead of 3.6,
+// 1 load instruction per lane instead of 3-4, no sigT index.  GPL = 4 keeps four groups per lane (two 256-bit
+// loads: {sigT, y[FAI]} and {y[FAI-1], y[FAI+1]}).  The records are a derived copy rebuilt by the library at every
+// launch from the canonical rows (build_records: 4 x the source array, a few microseconds), so uploads, row-range
+// transfers and external writes into the device arrays keep their meaning.  The arithmetic is attenuate_fast2 with
+// per-lane fit coefficients, i.e. bit-identical per intersection to attenuate_tracks<.., kMathFast, ..>.
+// ------------------------------------------------------------------------------
+struct __align__(32) Rec8 {
+    float2 a, b, c, d;
+};
+
+__device__ __forceinline__ Rec8 ldg256(const void *p)
+{
+    Rec8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.c.x), "=f"(r.c.y), "=f"(r.d.x), "=f"(r.d.y)
+                 : "l"(p));
+    return r;
+}
+
+template <int GPL>
+__global__ void build_records(const float *__restrict__ source, const float *__restrict__ sigT, float *__restrict__ rec,
+                              int64_t rows, int fai_count, int groups_pad)
+{
+    // one thread per (row, GPL groups): writes 8 * GPL/2 floats... GPL = 2: one 32-byte record; GPL = 4: two
+    const int per_row = groups_pad / GPL;
+    const int64_t n = rows * per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / per_row;
+        const int j = (int)(i - row * per_row);
+        const int64_t qsr = row / fai_count;
+        const int fai = (int)(row - qsr * fai_count);
+        const float *yc = source + row * groups_pad + j * GPL;
+        const float *st = sigT + qsr * groups_pad + j * GPL;
+        float *out = rec + i * (4 * GPL);
+        float m[GPL], c[GPL], p[GPL], s[GPL];
+#pragma unroll
+        for (int g = 0; g < GPL; ++g) {
+            s[g] = st[g];
+            c[g] = yc[g];
+            m[g] = fai > 0 ? yc[g - groups_pad] : 0.0f;
+            p[g] = fai < fai_count - 1 ? yc[g + groups_pad] : 0.0f;
+        }
+        if constexpr (GPL == 2) {
+            out[0] = s[0]; out[1] = s[1]; out[2] = m[0]; out[3] = m[1];
+            out[4] = c[0]; out[5] = c[1]; out[6] = p[0]; out[7] = p[1];
+        } else {
+            // {sigT[4], y[FAI][4]} {y[FAI-1][4], y[FAI+1][4]}
+#pragma unroll
+            for (int g = 0; g < 4; ++g) { out[g] = s[g]; out[4 + g] = c[g]; out[8 + g] = m[g]; out[12 + g] = p[g]; }
+        }
+    }
+}
+
+#ifndef SMK_MIN_BLOCKS_REC
+#define SMK_MIN_BLOCKS_REC SMK_MIN_BLOCKS_FAST
+#endif
+constexpr int kMinBlocksRec = SMK_MIN_BLOCKS_REC;
+
+// one segment of one lane of attenuate_record_tracks.  CHECK: the lane may be past its track's end (the stream's ragged
+// last track, or a warp slot without a track): it computes along with its warp-mates, tallies nothing, keeps its psi.
+template <int LPT, int GPL, int EXPM, bool F64, bool CHECK>
+__device__ __forceinline__ void record_segment(const char *rec, const float4 *s_fit, const float2 *s_pairs, float *tally,
+                                               double *tally64, uint32_t pidx, int sub, bool active,
+                                               typename LaneVec<GPL>::type &psi)
+{
+    typedef typename LaneVec<GPL>::type V;
+    const uint32_t idx = (pidx & ~(kRowFirst | kRowLast)) | (uint32_t)sub;
+    const char *r = ptr_add_index<true>(rec, idx * (16u * GPL));
+    // fit coefficients of the lane's segment type (tracks of different types share a warp): a 3-way broadcast
+    // read of a shared table instead of seven selects and the moves that feed them
+    const float4 *fit = s_fit + 2 * (pidx >> 30);
+    const float4 f0 = fit[0];
+    const float2 f1 = *reinterpret_cast<const float2 *>(fit + 1);
+    FitCoeffs fc;
+    fc.q0_d = f0.x; fc.q0_s = f0.y; fc.q1_d = f0.z; fc.q1_s = f0.w; fc.q2_s = f1.x;
+    fc.ds = Geometry::ds; fc.weight = Geometry::weight;
+    V t;
+    if constexpr (GPL == 2) {
+        const Rec8 q = ldg256(r);
+        float2 ps = psi;
+        attenuate_fast2<EXPM, kFitDynamic, false>(fc, q.b, q.c, q.d, q.a, s_pairs, ps, t);
+        if (!CHECK || active) psi = ps;                                       // kernel.c:331
+    } else {
+        const Rec8 q0 = ldg256(r), q1 = ldg256(r + 32);
+        float2 p_lo = make_float2(psi.x, psi.y), p_hi = make_float2(psi.z, psi.w), t_lo, t_hi;
+        attenuate_fast2<EXPM, kFitDynamic, false>(fc, q1.a, q0.c, q1.c, q0.a, s_pairs, p_lo, t_lo);
+        attenuate_fast2<EXPM, kFitDynamic, false>(fc, q1.b, q0.d, q1.d, q0.b, s_pairs, p_hi, t_hi);
+        if (!CHECK || active) psi = make_float4(p_lo.x, p_lo.y, p_hi.x, p_hi.y);
+        t = make_float4(t_lo.x, t_lo.y, t_hi.x, t_hi.y);
+    }
+    if (!CHECK || active) tally_lane<F64, true>(tally, tally64, idx, t);      // kernel.c:276
+}
+
+template <int LPT, int GPL, int EXPM, bool F64>
+__global__ void __launch_bounds__(kThreadsPerBlock, kMinBlocksRec)
+attenuate_record_tracks(const KernelArgs a)
+{
+    static_assert(LPT >= 1 && LPT <= 16 && (LPT & (LPT - 1)) == 0, "LPT must be a power of two");
+    static_assert(GPL == 2 || GPL == 4, "two or four groups per lane");
+    typedef typename LaneVec<GPL>::type V;
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    constexpr int kSlotsPerWarp = 32 / LPT;
+
+    __shared__ float2 s_pairs[kTableReach];
+    // {q0_d, q0_s, q1_d, q1_s} {q2_s, -, -, -} per segment type = pidx >> 30: interior, first, last, (no segment)
+    __shared__ float4 s_fit[8];
+    if (threadIdx.x < 4) {
+        const FitCoeffs f = fit_coeffs(threadIdx.x == 1, threadIdx.x == 2);
+        s_fit[2 * threadIdx.x] = make_float4(f.q0_d, f.q0_s, f.q1_d, f.q1_s);
+        s_fit[2 * threadIdx.x + 1] = make_float4(f.q2_s, 0.0f, 0.0f, 0.0f);
+    }
+    if constexpr (EXPM == kExpTable) {
+        if (threadIdx.x < kTableReach) s_pairs[threadIdx.x] = c_exp_table.pairs[threadIdx.x];
+    }
+    __syncthreads();
+    int lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const int sub = lane & (LPT - 1);
+    const int64_t warp_global = (int64_t)blockIdx.x * (kThreadsPerBlock / 32) + (threadIdx.x >> 5);
+    const uint32_t F = (uint32_t)a.fai_count;
+    const int p = a.seg_per_track;
+    const char *const rec = reinterpret_cast<const char *>(a.records);
+    float *const tally = warp_tally(a, warp_global);
+    const int64_t n_work = a.track_end - a.track_begin;
+    unsigned long long checksum = 0ull;
+
+    for (int64_t wbase = claim_work(a, lane, kSlotsPerWarp); wbase < n_work; wbase = claim_work(a, lane, kSlotsPerWarp)) {
+        const int64_t work = wbase + (lane / LPT);
+        const bool tvalid = work < n_work;
+        const int64_t track = a.track_begin + work;
+        const int64_t s0 = track * p;
+        int nseg = 0;
+        if (tvalid) {
+            const int64_t left = a.segments - s0;
+            nseg = left < p ? (int)left : p;
+        }
+
+        // incoming angular flux of the track (kernel.c:29-30): one Philox block covers 4 groups
+        V psi;
+        if constexpr (GPL == 4) {
+            const u32x4 r = stream_words(a.keys, (uint64_t)track, (uint32_t)sub, kDomainPsi);
+            psi = make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+        } else {
+            const u32x4 r = stream_words(a.keys, (uint64_t)track, (uint32_t)(sub >> 1), kDomainPsi);
+            psi = (sub & 1) ? make_float2(u01(r.z), u01(r.w)) : make_float2(u01(r.x), u01(r.y));
+        }
+
+        const int nseg_warp = __reduce_max_sync(kFull, nseg);
+        const bool even = __all_sync(kFull, nseg == nseg_warp);      // every slot of the warp has a full-length track
+        uint64_t seg = (uint64_t)s0 + (uint64_t)sub;                 // the segment this lane hashes in the next batch
+        for (int b = 0; b < nseg_warp; b += LPT, seg += LPT) {
+            // each lane of the track draws the ids of one of the next LPT segments: idx = row * LPT (the lane's
+            // element of the record row and of the tally row once `| sub` is added) + the two type flags.
+            // Lanes without a segment keep row 0 with both flags: a valid address, nothing is tallied.
+            uint32_t my_idx = kRowFirst | kRowLast;
+            if (b + sub < nseg) {
+                const u32x4 w = stream_words(a.keys, seg, 0u, kDomainSegment);
+                const uint32_t qsr = fastmod(w.x >> 1, a.mod_regions);                   // kernel.c:47
+                const uint32_t fai = fastmod(w.y >> 1, a.mod_fai);                       // kernel.c:50
+                my_idx = ((qsr * F + fai) * (uint32_t)LPT) | (fai == 0u ? kRowFirst : 0u) | (fai == F - 1u ? kRowLast : 0u);
+                checksum += checksum_term(qsr, fai, F, seg);
+            }
+            const int count = (nseg_warp - b) < LPT ? (nseg_warp - b) : LPT;
+            if (even) {
+#pragma unroll 2
+                for (int k = 0; k < count; ++k)
+                    record_segment<LPT, GPL, EXPM, F64, false>(rec, s_fit, s_pairs, tally, a.tally64,
+                                                               __shfl_sync(kFull, my_idx, k, LPT), sub, true, psi);
+            } else {
+                for (int k = 0; k < count; ++k)
+                    record_segment<LPT, GPL, EXPM, F64, true>(rec, s_fit, s_pairs, tally, a.tally64,
+                                                              __shfl_sync(kFull, my_idx, k, LPT), sub, (b + k) < nseg, psi);
+            }
+        }
+
+        if (a.psi_out != nullptr && tvalid)
+            reinterpret_cast<V *>(a.psi_out)[(track - a.track_begin) * LPT + sub] = psi;
+    }
+
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) checksum += __shfl_xor_sync(kFull, checksum, off);
     if (lane == 0 && checksum != 0ull) atomicAdd(a.checksum, checksum);

@@ -219,9 +219,11 @@ SMK_HD SegmentIds segment_ids(uint64_t seed, uint64_t seg, const FastMod &mod_re
 }
 
 // weight of segment s in the indexing fingerprint (include/smk.h: smk_download_checksum)
+// (row + 1 < 2^31: smk_create checks regions * intervals < 2^30, so the first factor fits 32 bits and the term is ONE
+// 32 x 32 -> 64-bit multiply-add on the device instead of a 64 x 32-bit product)
 SMK_HD uint64_t checksum_term(uint32_t qsr, uint32_t fai, uint32_t fai_count, uint64_t seg)
 {
-    return ((uint64_t)qsr * fai_count + fai + 1u) * ((seg & 0xFFFFu) + 1u);
+    return (uint64_t)(qsr * fai_count + fai + 1u) * (uint64_t)(((uint32_t)seg & 0xFFFFu) + 1u);
 }
 
 }  // namespace smk

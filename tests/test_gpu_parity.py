@@ -527,6 +527,50 @@ def test_wide_and_32bit_address_forms_agree(smk, oracle, monkeypatch, G, geom):
 
 
 # ---------------------------------------------------------------------------------------
+# gather records of the sub-warp shapes (<= 32 groups)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("G,N,p", [(3, 30_000, 10), (7, 100_000, 100), (13, 30_011, 37), (29, 30_000, 100), (32, 20_005, 50)])
+def test_record_kernel_matches_general_kernel(smk, oracle, monkeypatch, G, N, p):
+    """Up to 32 groups the FAST sweep reads gather records {sigT, y[FAI-1], y[FAI], y[FAI+1]} (one 256-bit load per
+    lane and segment, attenuate_record_tracks) rebuilt from the canonical rows at every launch.  Same arithmetic as
+    the general kernel (SMK_RECORDS=0): psi per track must agree bit for bit, for both record shapes (2 and 4
+    groups per lane), also after the rows were replaced through the row-range upload path; ragged last tracks."""
+    R, F, seed = 60, 5, 81
+    src, flux0, sig = oracle.fill(R, F, G, seed)
+    src2, _, sig2 = oracle.fill(R, F, G, seed + 1)
+    want = flux0.copy()
+    _, chk_want = oracle.run(src, want, sig, N, p, seed, nthreads=0)
+    want2 = flux0.copy()
+    oracle.run(src2, want2, sig2, N, p, seed, nthreads=0)
+    out = {}
+    for mode in ("0", "2", "4"):
+        monkeypatch.setenv("SMK_RECORDS", mode)
+        I = make_input(smk, R, F, G, N, p, seed, "poly", "fast")
+        with smk.Context(I, keep_psi=True) as ctx:
+            ctx.upload(src, flux0, sig)
+            name = ctx.kernel_name
+            ctx.run()
+            first = (ctx.download_flux(), ctx.download_psi(ctx.n_tracks), ctx.checksum())
+            # new rows through the partial-upload path: the records must follow
+            half = (R * F) // 2 + 1          # splits a region's block of F rows
+            rows2 = np.ascontiguousarray(src2.reshape(R * F, G))
+            ctx.upload_rows_async(smk.ARRAY_SOURCE, 0, half, rows2[:half])
+            ctx.upload_rows_async(smk.ARRAY_SOURCE, half, R * F - half, rows2[half:])
+            ctx.upload_rows_async(smk.ARRAY_SIGT, 0, R, sig2)
+            ctx.reset_tallies()
+            ctx.run()
+            second = (ctx.download_flux(), ctx.download_psi(ctx.n_tracks))
+        assert ("attenuate_record_tracks<%s groups/lane" % mode in name) == (mode != "0"), name
+        assert first[2] == chk_want
+        assert l2rel(first[0], want) <= TOL_FAST
+        assert l2rel(second[0], want2) <= TOL_FAST
+        out[mode] = (first[1], second[1])
+    for mode in ("2", "4"):
+        assert np.array_equal(bits(out[mode][0]), bits(out["0"][0])), mode
+        assert np.array_equal(bits(out[mode][1]), bits(out["0"][1])), mode
+
+
+# ---------------------------------------------------------------------------------------
 # degenerate cross sections: the values the mini-app's own fill can produce at the small end
 # ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("G", [128, 64, 7])
