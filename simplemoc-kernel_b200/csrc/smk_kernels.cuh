@@ -558,6 +558,10 @@ __global__ void build_records(const float *__restrict__ source, const float *__r
 #define SMK_MIN_BLOCKS_REC SMK_MIN_BLOCKS_FAST
 #endif
 constexpr int kMinBlocksRec = SMK_MIN_BLOCKS_REC;
+#ifndef SMK_REC_UNROLL
+#define SMK_REC_UNROLL 2
+#endif
+constexpr int kRecordUnroll = SMK_REC_UNROLL;     // segment loop of attenuate_record_tracks (tuning knob)
 
 // one segment of one lane of attenuate_record_tracks.  CHECK: the lane may be past its track's end (the stream's ragged
 // last track, or a warp slot without a track): it computes along with its warp-mates, tallies nothing, keeps its psi.
@@ -665,7 +669,7 @@ attenuate_record_tracks(const KernelArgs a)
             }
             const int count = (nseg_warp - b) < LPT ? (nseg_warp - b) : LPT;
             if (even) {
-#pragma unroll 2
+#pragma unroll kRecordUnroll
                 for (int k = 0; k < count; ++k)
                     record_segment<LPT, GPL, EXPM, F64, false>(rec, s_fit, s_pairs, tally, a.tally64,
                                                                __shfl_sync(kFull, my_idx, k, LPT), sub, true, psi);
