@@ -495,7 +495,7 @@ attenuate_tracks(const KernelArgs a)
 //
 // With few groups a track is a handful of lanes and every lane group gathers its own rows: each of the 3.6 row
 // loads + 1 RED per (track, segment) is its own L1 wavefront (one 32-byte sector per lane pair), and at 7 groups
-// the general kernel sits against the L1 wavefront rate (L1/TEX 89 % busy, profiles/ncu_r02_g7.md) with the
+// the general kernel sits against the L1 wavefront rate (L1/TEX 89 % busy, profiles/ncu_r02_g7_general.md) with the
 // FMA pipe half idle.  build_records lays everything one (segment, pair of groups) reads side by side,
 //     rec[row = QSR * F + FAI][j] = { sigT[QSR][2j..2j+1], y[FAI-1][2j..2j+1], y[FAI][2j..2j+1], y[FAI+1][2j..2j+1] }
 // (32 bytes; the missing neighbour of an edge interval is 0, exactly what the general kernel substitutes), so a lane

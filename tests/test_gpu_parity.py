@@ -570,6 +570,29 @@ def test_record_kernel_matches_general_kernel(smk, oracle, monkeypatch, G, N, p)
         assert np.array_equal(bits(out[mode][1]), bits(out["0"][1])), mode
 
 
+@pytest.mark.parametrize("exp_mode", ["mufu", "glibc", "table"])
+def test_record_kernel_other_exponentials_and_f64_tallies(smk, oracle, monkeypatch, exp_mode):
+    """Every exponential of the record kernel against the general kernel: psi bit-identical, and with the f64 tally
+    accumulators (order-independent sums of identical per-intersection tallies) the flux is bit-identical too."""
+    R, F, G, N, p, seed = 80, 5, 7, 40_000, 100, 83
+    src, flux0, sig = oracle.fill(R, F, G, seed)
+    out = {}
+    for mode in ("0", ""):
+        if mode:
+            monkeypatch.setenv("SMK_RECORDS", mode)
+        else:
+            monkeypatch.delenv("SMK_RECORDS", raising=False)
+        I = make_input(smk, R, F, G, N, p, seed, exp_mode, "fast", tally_f64=True)
+        with smk.Context(I, keep_psi=True) as ctx:
+            ctx.upload(src, flux0, sig)
+            assert ("attenuate_record_tracks" in ctx.kernel_name) == (mode == ""), ctx.kernel_name
+            ctx.run()
+            out[mode] = (ctx.download_flux(), ctx.download_psi(ctx.n_tracks), ctx.checksum())
+    assert out["0"][2] == out[""][2]
+    assert np.array_equal(bits(out["0"][1]), bits(out[""][1]))
+    assert np.array_equal(bits(out["0"][0]), bits(out[""][0]))
+
+
 # ---------------------------------------------------------------------------------------
 # degenerate cross sections: the values the mini-app's own fill can produce at the small end
 # ---------------------------------------------------------------------------------------
