@@ -23,7 +23,8 @@ uploads / downloads 1/N of the rows and the replicas are completed over NVLink.
 Roofline: the BINDING resource per leg -- the FP32 pipe for the L2-resident working sets (38 MB of source
 data live in the 126 MB L2, measured DRAM traffic per launch is under `traffic`), HBM for the HBM-resident
 regime.  The reference arm times the UNMODIFIED reference CPU run_kernel (oracle/_ref/libref_ofast.so =
-/root/reference/src/cpu built with its Makefile's gnu flags) on all host cores.
+/root/reference/src/cpu built with its Makefile's gnu flags) on all host cores; the config 3 and config 4 legs
+carry the same reference timed at their own shape (`cpu_reference`).
 """
 import argparse
 import json
@@ -574,6 +575,18 @@ def main_ours(a):
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu = time_reference(a, steps=2, warmup=1, segments=20_000_000)
         cpu.pop("ms_per_step", None)
+        # the reference CPU beside the other BASELINE shapes too (bounded samples, ~1 s each)
+        for leg in legs:
+            shape = {"config3_7_groups": dict(egroups=7), "config4_64_groups_14_regions": dict(egroups=64, regions_2d=10)}.get(leg["name"])
+            if shape is None:
+                continue
+            try:
+                la = argparse.Namespace(**{**vars(a), **shape})
+                r = time_reference(la, steps=1, warmup=1, segments=20_000_000)
+                leg["cpu_reference"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                        "sample": r["sample"]}
+            except Exception as e:      # the leg's GPU numbers stand on their own
+                leg["cpu_reference"] = {"unavailable": str(e)[:200]}
         try:   # the same sources built for AVX2+FMA (-march=x86-64-v3): the "fair" CPU figure
             from oracle.oracle import Reference
             if Reference.available("v3"):
