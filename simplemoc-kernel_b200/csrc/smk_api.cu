@@ -100,7 +100,9 @@ typedef void (*AttenuateFn)(const KernelArgs);
 // groups per lane of attenuate_record_tracks: four (two 256-bit loads per lane and segment) from 5 groups up, two for
 // 1..4 groups, where four would leave one lane per track (measured, profiles/ab_r02.md: 29 groups 5.63e11 vs 5.42e11,
 // 13 groups 4.62e11 vs 4.49e11, 7 groups equal, 3 groups 2.25e11 vs 2.80e11)
-static int record_groups_per_lane(int groups_pad) { return groups_pad >= 8 ? 4 : 2; }
+// With per-segment geometry the 5..8-group shape is faster with two (3.59e11 vs 3.46e11 at 7 groups; 17..32 groups:
+// 5.05e11 with four vs 4.88e11).
+static int record_groups_per_lane(int groups_pad, bool geom) { return groups_pad > (geom ? 8 : 4) ? 4 : 2; }
 
 struct KernelChoice {
     AttenuateFn fn;
@@ -169,27 +171,50 @@ static AttenuateFn pick_warp_track(int expm, bool f64, bool geom, bool a32)
     return geom ? pick_warp_track_exp<GPL, false, true, false>(expm) : pick_warp_track_exp<GPL, false, false, false>(expm);
 }
 
-// sub-warp tracks from gather records (<= 32 groups, FAST, constant geometry); lpt = lanes per track = G_pad / gpl
-template <int LPT, int GPL, bool F64>
+// sub-warp tracks from gather records (<= 32 groups, FAST); lpt = lanes per track = G_pad / gpl
+template <int LPT, int GPL, bool F64, bool GEOM>
 static AttenuateFn pick_record_exp(int expm)
 {
     switch (expm) {
-        case kExpPoly: return attenuate_record_tracks<LPT, GPL, kExpPoly, F64>;
-        case kExpPolyWide: return attenuate_record_tracks<LPT, GPL, kExpPolyWide, F64>;
-        case kExpMufu: return attenuate_record_tracks<LPT, GPL, kExpMufu, F64>;
-        case kExpGlibc: return attenuate_record_tracks<LPT, GPL, kExpGlibc, F64>;
-        case kExpTable: return attenuate_record_tracks<LPT, GPL, kExpTable, F64>;
+        case kExpPoly: return attenuate_record_tracks<LPT, GPL, kExpPoly, F64, GEOM>;
+        case kExpPolyWide: return attenuate_record_tracks<LPT, GPL, kExpPolyWide, F64, GEOM>;
+        case kExpMufu: return attenuate_record_tracks<LPT, GPL, kExpMufu, F64, GEOM>;
+        case kExpGlibc: return attenuate_record_tracks<LPT, GPL, kExpGlibc, F64, GEOM>;
+        case kExpTable: return attenuate_record_tracks<LPT, GPL, kExpTable, F64, GEOM>;
     }
     return nullptr;
 }
 
-template <int GPL>
-static AttenuateFn pick_record(int groups_pad, int expm, bool f64)
+// ALL = every exponential (the shapes the library uses, record_groups_per_lane); otherwise POLY only: the other record
+// shape of each group count exists for the A/B knob SMK_RECORDS and the cross-check test
+template <int LPT, int GPL, bool F64, bool GEOM, bool ALL>
+static AttenuateFn pick_record_modes(int expm)
 {
-    switch (groups_pad / GPL) {
-#define SMK_PICK(L) case L: return f64 ? pick_record_exp<L, GPL, true>(expm) : pick_record_exp<L, GPL, false>(expm);
-        SMK_PICK(1) SMK_PICK(2) SMK_PICK(4) SMK_PICK(8) SMK_PICK(16)
-#undef SMK_PICK
+    if constexpr (ALL) return pick_record_exp<LPT, GPL, F64, GEOM>(expm);
+    if (expm == kExpPoly) return attenuate_record_tracks<LPT, GPL, kExpPoly, F64, GEOM>;
+    if (expm == kExpPolyWide) return attenuate_record_tracks<LPT, GPL, kExpPolyWide, F64, GEOM>;
+    return nullptr;
+}
+
+template <int LPT, int GPL, bool ALL>
+static AttenuateFn pick_record_flags(int expm, bool f64, bool geom)
+{
+    if (f64) return geom ? pick_record_modes<LPT, GPL, true, true, ALL>(expm) : pick_record_modes<LPT, GPL, true, false, ALL>(expm);
+    return geom ? pick_record_modes<LPT, GPL, false, true, ALL>(expm) : pick_record_modes<LPT, GPL, false, false, ALL>(expm);
+}
+
+static AttenuateFn pick_record(int groups_pad, int gpl, int expm, bool f64, bool geom)
+{
+    const int key = groups_pad * 10 + gpl;
+    switch (key) {
+        case 42: return pick_record_flags<2, 2, true>(expm, f64, geom);      // 1..4 groups
+        case 44: return pick_record_flags<1, 4, false>(expm, f64, geom);
+        case 84: return pick_record_flags<2, 4, true>(expm, f64, geom);      // 5..8 groups (config 3)
+        case 82: return pick_record_flags<4, 2, true>(expm, f64, geom);       // the library's shape with per-segment geometry
+        case 164: return pick_record_flags<4, 4, true>(expm, f64, geom);     // 9..16 groups
+        case 162: return pick_record_flags<8, 2, false>(expm, f64, geom);
+        case 324: return pick_record_flags<8, 4, true>(expm, f64, geom);     // 17..32 groups
+        case 322: return pick_record_flags<16, 2, false>(expm, f64, geom);
     }
     return nullptr;
 }
@@ -329,7 +354,7 @@ static int select_kernel(smk_ctx *c)
     const bool a32 = (uint64_t)c->rows * c->shape.groups_pad * sizeof(float) < (1ull << 32) && !(force64 && force64[0] == '1');
     bool warp_track32 = false;
     if (!fn && c->d_records) {
-        fn = c->rec_gpl == 2 ? pick_record<2>(c->shape.groups_pad, expm, f64) : pick_record<4>(c->shape.groups_pad, expm, f64);
+        fn = pick_record(c->shape.groups_pad, c->rec_gpl, expm, f64, geom);
         family = c->rec_gpl == 2 ? "attenuate_record_tracks<2 groups/lane" : "attenuate_record_tracks<4 groups/lane";
     }
     if (!fn) {
@@ -450,15 +475,18 @@ int smk_create(const smk_params *p, smk_ctx **out)
         e = cudaMalloc(&c->d_tally64, 2 * slab);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tally64, 0, 2 * slab, c->stream);
     }
-    // <= 32 groups, FAST, constant geometry: the sweep reads gather records (attenuate_record_tracks), 4 x the
+    // <= 32 groups, FAST: the sweep reads gather records (attenuate_record_tracks), 4 x the
     // source array, rebuilt from the canonical rows at every launch.  SMK_RECORDS=0 keeps the general kernel
     // (A/B and the cross-check test), =2 / =4 selects the groups per lane.
     {
-        int gpl = record_groups_per_lane(shape.groups_pad);
+        const int gpl_default = record_groups_per_lane(shape.groups_pad, (p->flags & SMK_FLAG_SEGMENT_GEOMETRY) != 0);
+        int gpl = gpl_default;
         if (const char *r = getenv("SMK_RECORDS")) gpl = atoi(r);
         const bool eligible = shape.nchunk == 1 && shape.groups_pad <= 32 && p->math_mode == kMathFast &&
-                              !(p->flags & SMK_FLAG_SEGMENT_GEOMETRY) && slab * 4 < (1ull << 32) &&
+                              slab * 4 < (1ull << 32) &&
                               c->rows * (shape.groups_pad / 2) < (1ll << 30);
+        // the non-default record shape is compiled for the POLY exponential only
+        if ((gpl == 2 || gpl == 4) && gpl != gpl_default && p->exp_mode != SMK_EXP_POLY) gpl = gpl_default;
         if (eligible && (gpl == 2 || gpl == 4)) {
             c->rec_gpl = gpl;
             if (e == cudaSuccess) e = cudaMalloc(&c->d_records, slab * 4);

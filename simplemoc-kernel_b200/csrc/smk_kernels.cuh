@@ -4,8 +4,8 @@
 //       attenuate_segment (/root/reference/src/cpu/kernel.c:43-55, 75-333), ONE WARP PER TRACK, FAST
 //       arithmetic.  GPL = energy groups per lane: 4 for 65..128 groups (128-bit loads, red.v4), 2 for
 //       33..64 groups (64-bit loads, red.v2).
-//   attenuate_record_tracks<LPT, GPL, EXPM, F64> <= 32 groups, FAST, constant geometry: sub-warp tracks fed by one
-//       256-bit load per lane and segment from gather records (build_records)
+//   attenuate_record_tracks<LPT, GPL, EXPM, F64, GEOM> <= 32 groups, FAST: sub-warp tracks fed by one or two
+//       256-bit loads per lane and segment from gather records (build_records)
 //   attenuate_tracks<LPT, NCHUNK, MATH, EXPM, GEOM> the general kernel: sub-warp tracks for <= 32 groups,
 //       blocks of 256 groups for > 128 groups (any group count), and the STRICT verification arithmetic
 //   fill_rows                                    device-side deterministic fill
@@ -490,8 +490,8 @@ attenuate_tracks(const KernelArgs a)
 }
 
 // ------------------------------------------------------------------------------
-// attenuate_record_tracks<LPT, GPL, EXPM, F64>: sub-warp tracks (G_pad <= 32), FAST arithmetic, constant
-// geometry, fed from GATHER RECORDS instead of the row arrays.
+// attenuate_record_tracks<LPT, GPL, EXPM, F64, GEOM>: sub-warp tracks (G_pad <= 32), FAST arithmetic, fed from
+// GATHER RECORDS instead of the row arrays.
 //
 // With few groups a track is a handful of lanes and every lane group gathers its own rows: each of the 3.6 row
 // loads + 1 RED per (track, segment) is its own L1 wavefront (one 32-byte sector per lane pair), and at 7 groups
@@ -506,6 +506,11 @@ attenuate_tracks(const KernelArgs a)
 // launch from the canonical rows (build_records: 4 x the source array, a few microseconds), so uploads, row-range
 // transfers and external writes into the device arrays keep their meaning.  The arithmetic is attenuate_fast2 with
 // per-lane fit coefficients, i.e. bit-identical per intersection to attenuate_tracks<.., kMathFast, ..>.
+// The coefficients come from shared memory: with the constant geometry a 4-entry table indexed by the segment type
+// (tracks of different types share a warp); with per-segment geometry (GEOM) the lane that hashes a segment derives
+// them once from stream words 2,3 (segment_geometry + fit_coeffs_geom, type folded in) and parks them in its slot,
+// and the lanes of the track read the slot of the step's hashing lane (the general kernel makes every lane derive
+// them from shuffled words): 7 groups 3.29e11 -> 3.59e11, 29 groups 4.12e11 -> 5.05e11 (profiles/ab_r02.md r02o).
 // ------------------------------------------------------------------------------
 struct __align__(32) Rec8 {
     float2 a, b, c, d;
@@ -565,40 +570,43 @@ constexpr int kRecordUnroll = SMK_REC_UNROLL;     // segment loop of attenuate_r
 
 // one segment of one lane of attenuate_record_tracks.  CHECK: the lane may be past its track's end (the stream's ragged
 // last track, or a warp slot without a track): it computes along with its warp-mates, tallies nothing, keeps its psi.
-template <int LPT, int GPL, int EXPM, bool F64, bool CHECK>
-__device__ __forceinline__ void record_segment(const char *rec, const float4 *s_fit, const float2 *s_pairs, float *tally,
+// `fit` points at the coefficients of the segment: {q0_d, q0_s, q1_d, q1_s} {q2_s, ds, weight, -}
+template <int LPT, int GPL, int EXPM, bool F64, bool GEOM, bool CHECK>
+__device__ __forceinline__ void record_segment(const char *rec, const float4 *fit, const float2 *s_pairs, float *tally,
                                                double *tally64, uint32_t pidx, int sub, bool active,
                                                typename LaneVec<GPL>::type &psi)
 {
     typedef typename LaneVec<GPL>::type V;
     const uint32_t idx = (pidx & ~(kRowFirst | kRowLast)) | (uint32_t)sub;
     const char *r = ptr_add_index<true>(rec, idx * (16u * GPL));
-    // fit coefficients of the lane's segment type (tracks of different types share a warp): a 3-way broadcast
-    // read of a shared table instead of seven selects and the moves that feed them
-    const float4 *fit = s_fit + 2 * (pidx >> 30);
     const float4 f0 = fit[0];
-    const float2 f1 = *reinterpret_cast<const float2 *>(fit + 1);
     FitCoeffs fc;
-    fc.q0_d = f0.x; fc.q0_s = f0.y; fc.q1_d = f0.z; fc.q1_s = f0.w; fc.q2_s = f1.x;
-    fc.ds = Geometry::ds; fc.weight = Geometry::weight;
+    fc.q0_d = f0.x; fc.q0_s = f0.y; fc.q1_d = f0.z; fc.q1_s = f0.w;
+    if constexpr (GEOM) {
+        const float4 f1 = fit[1];
+        fc.q2_s = f1.x; fc.ds = f1.y; fc.weight = f1.z;
+    } else {
+        fc.q2_s = *reinterpret_cast<const float *>(fit + 1);
+        fc.ds = Geometry::ds; fc.weight = Geometry::weight;
+    }
     V t;
     if constexpr (GPL == 2) {
         const Rec8 q = ldg256(r);
         float2 ps = psi;
-        attenuate_fast2<EXPM, kFitDynamic, false>(fc, q.b, q.c, q.d, q.a, s_pairs, ps, t);
+        attenuate_fast2<EXPM, kFitDynamic, GEOM>(fc, q.b, q.c, q.d, q.a, s_pairs, ps, t);
         if (!CHECK || active) psi = ps;                                       // kernel.c:331
     } else {
         const Rec8 q0 = ldg256(r), q1 = ldg256(r + 32);
         float2 p_lo = make_float2(psi.x, psi.y), p_hi = make_float2(psi.z, psi.w), t_lo, t_hi;
-        attenuate_fast2<EXPM, kFitDynamic, false>(fc, q1.a, q0.c, q1.c, q0.a, s_pairs, p_lo, t_lo);
-        attenuate_fast2<EXPM, kFitDynamic, false>(fc, q1.b, q0.d, q1.d, q0.b, s_pairs, p_hi, t_hi);
+        attenuate_fast2<EXPM, kFitDynamic, GEOM>(fc, q1.a, q0.c, q1.c, q0.a, s_pairs, p_lo, t_lo);
+        attenuate_fast2<EXPM, kFitDynamic, GEOM>(fc, q1.b, q0.d, q1.d, q0.b, s_pairs, p_hi, t_hi);
         if (!CHECK || active) psi = make_float4(p_lo.x, p_lo.y, p_hi.x, p_hi.y);
         t = make_float4(t_lo.x, t_lo.y, t_hi.x, t_hi.y);
     }
     if (!CHECK || active) tally_lane<F64, true>(tally, tally64, idx, t);      // kernel.c:276
 }
 
-template <int LPT, int GPL, int EXPM, bool F64>
+template <int LPT, int GPL, int EXPM, bool F64, bool GEOM>
 __global__ void __launch_bounds__(kThreadsPerBlock, kMinBlocksRec)
 attenuate_record_tracks(const KernelArgs a)
 {
@@ -607,14 +615,21 @@ attenuate_record_tracks(const KernelArgs a)
     typedef typename LaneVec<GPL>::type V;
     constexpr unsigned kFull = 0xFFFFFFFFu;
     constexpr int kSlotsPerWarp = 32 / LPT;
+    constexpr int kWarps = kThreadsPerBlock / 32;
 
     __shared__ float2 s_pairs[kTableReach];
-    // {q0_d, q0_s, q1_d, q1_s} {q2_s, -, -, -} per segment type = pidx >> 30: interior, first, last, (no segment)
-    __shared__ float4 s_fit[8];
-    if (threadIdx.x < 4) {
-        const FitCoeffs f = fit_coeffs(threadIdx.x == 1, threadIdx.x == 2);
-        s_fit[2 * threadIdx.x] = make_float4(f.q0_d, f.q0_s, f.q1_d, f.q1_s);
-        s_fit[2 * threadIdx.x + 1] = make_float4(f.q2_s, 0.0f, 0.0f, 0.0f);
+    // constant geometry: {q0_d, q0_s, q1_d, q1_s} {q2_s, -, -, -} per segment type = pidx >> 30 (interior, first, last,
+    // no segment): tracks of different types share a warp, and a 3-way broadcast read of this table replaces seven
+    // selects and the moves that feed them.
+    // GEOM: per warp and hashing lane, the coefficients of that lane's segment of the batch (its type folded in),
+    // {q0_d, q0_s, q1_d, q1_s} {q2_s, ds, weight, -}: derived once by the lane that hashed the segment.
+    __shared__ float4 s_fit[GEOM ? kWarps * 64 : 8];
+    if constexpr (!GEOM) {
+        if (threadIdx.x < 4) {
+            const FitCoeffs f = fit_coeffs(threadIdx.x == 1, threadIdx.x == 2);
+            s_fit[2 * threadIdx.x] = make_float4(f.q0_d, f.q0_s, f.q1_d, f.q1_s);
+            s_fit[2 * threadIdx.x + 1] = make_float4(f.q2_s, 0.0f, 0.0f, 0.0f);
+        }
     }
     if constexpr (EXPM == kExpTable) {
         if (threadIdx.x < kTableReach) s_pairs[threadIdx.x] = c_exp_table.pairs[threadIdx.x];
@@ -623,7 +638,9 @@ attenuate_record_tracks(const KernelArgs a)
     int lane;
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
     const int sub = lane & (LPT - 1);
-    const int64_t warp_global = (int64_t)blockIdx.x * (kThreadsPerBlock / 32) + (threadIdx.x >> 5);
+    const int64_t warp_global = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    float4 *const my_fit = s_fit + (GEOM ? ((threadIdx.x >> 5) * 64 + 2 * lane) : 0);            // this lane's slot (GEOM)
+    const float4 *const track_fit = s_fit + (GEOM ? ((threadIdx.x >> 5) * 64 + 2 * (lane - sub)) : 0);   // slot of the track's lane 0
     const uint32_t F = (uint32_t)a.fai_count;
     const int p = a.seg_per_track;
     const char *const rec = reinterpret_cast<const char *>(a.records);
@@ -666,18 +683,32 @@ attenuate_record_tracks(const KernelArgs a)
                 const uint32_t fai = fastmod(w.y >> 1, a.mod_fai);                       // kernel.c:50
                 my_idx = ((qsr * F + fai) * (uint32_t)LPT) | (fai == 0u ? kRowFirst : 0u) | (fai == F - 1u ? kRowLast : 0u);
                 checksum += checksum_term(qsr, fai, F, seg);
+                if constexpr (GEOM) {
+                    const FitCoeffs f = fit_coeffs_geom(segment_geometry(a.geom, w.z, w.w), a.mesh, fai == 0u, fai == F - 1u);
+                    my_fit[0] = make_float4(f.q0_d, f.q0_s, f.q1_d, f.q1_s);
+                    my_fit[1] = make_float4(f.q2_s, f.ds, f.weight, 0.0f);
+                }
+            } else if constexpr (GEOM) {
+                my_fit[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                my_fit[1] = make_float4(0.0f, 1.0f, 0.0f, 0.0f);
             }
+            if constexpr (GEOM) __syncwarp();
             const int count = (nseg_warp - b) < LPT ? (nseg_warp - b) : LPT;
             if (even) {
 #pragma unroll kRecordUnroll
-                for (int k = 0; k < count; ++k)
-                    record_segment<LPT, GPL, EXPM, F64, false>(rec, s_fit, s_pairs, tally, a.tally64,
-                                                               __shfl_sync(kFull, my_idx, k, LPT), sub, true, psi);
+                for (int k = 0; k < count; ++k) {
+                    const uint32_t pidx = __shfl_sync(kFull, my_idx, k, LPT);
+                    record_segment<LPT, GPL, EXPM, F64, GEOM, false>(rec, GEOM ? track_fit + 2 * k : s_fit + 2 * (pidx >> 30), s_pairs,
+                                                                     tally, a.tally64, pidx, sub, true, psi);
+                }
             } else {
-                for (int k = 0; k < count; ++k)
-                    record_segment<LPT, GPL, EXPM, F64, true>(rec, s_fit, s_pairs, tally, a.tally64,
-                                                              __shfl_sync(kFull, my_idx, k, LPT), sub, (b + k) < nseg, psi);
+                for (int k = 0; k < count; ++k) {
+                    const uint32_t pidx = __shfl_sync(kFull, my_idx, k, LPT);
+                    record_segment<LPT, GPL, EXPM, F64, GEOM, true>(rec, GEOM ? track_fit + 2 * k : s_fit + 2 * (pidx >> 30), s_pairs,
+                                                                    tally, a.tally64, pidx, sub, (b + k) < nseg, psi);
+                }
             }
+            if constexpr (GEOM) __syncwarp();       // everyone is done with the slots before the next batch overwrites them
         }
 
         if (a.psi_out != nullptr && tvalid)

@@ -570,6 +570,32 @@ def test_record_kernel_matches_general_kernel(smk, oracle, monkeypatch, G, N, p)
         assert np.array_equal(bits(out[mode][1]), bits(out["0"][1])), mode
 
 
+@pytest.mark.parametrize("G,N,p", [(7, 50_000, 100), (29, 20_003, 37), (3, 20_000, 10)])
+def test_record_kernel_per_segment_geometry(smk, oracle, monkeypatch, G, N, p):
+    """Per-segment geometry through the record kernel: the lane that hashes a segment derives its fit coefficients
+    once and parks them in shared memory.  psi per track bit-identical to the general kernel (whose lanes each
+    derive them from the shuffled stream words), flux within the gate of the parametrised oracle."""
+    R, F, seed = 70, 5, 85
+    g7 = geometry7(REFERENCE_GEOMETRY, 0.25)
+    src, flux0, sig = oracle.fill(R, F, G, seed)
+    want = flux0.copy()
+    _, chk_want = oracle.run(src, want, sig, N, p, seed, nthreads=0, flags=GEOM, geom7=g7)
+    out = {}
+    for mode in ("0", "2", "4"):
+        monkeypatch.setenv("SMK_RECORDS", mode)
+        I = make_input(smk, R, F, G, N, p, seed, "poly", "fast", geom=(REFERENCE_GEOMETRY, 0.25))
+        with smk.Context(I, keep_psi=True) as ctx:
+            ctx.upload(src, flux0, sig)
+            name = ctx.kernel_name
+            ctx.run()
+            out[mode] = (ctx.download_flux(), ctx.download_psi(ctx.n_tracks), ctx.checksum())
+        assert ("attenuate_record_tracks" in name) == (mode != "0") and "per-segment" in name, name
+        assert out[mode][2] == chk_want
+        assert l2rel(out[mode][0], want) <= TOL_FAST
+    for mode in ("2", "4"):
+        assert np.array_equal(bits(out[mode][1]), bits(out["0"][1])), mode
+
+
 @pytest.mark.parametrize("exp_mode", ["mufu", "glibc", "table"])
 def test_record_kernel_other_exponentials_and_f64_tallies(smk, oracle, monkeypatch, exp_mode):
     """Every exponential of the record kernel against the general kernel: psi bit-identical, and with the f64 tally
