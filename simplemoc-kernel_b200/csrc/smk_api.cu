@@ -219,6 +219,19 @@ static AttenuateFn pick_record(int groups_pad, int gpl, int expm, bool f64, bool
     return nullptr;
 }
 
+// 33..64 groups: one track per warp from gather records (constant geometry, f32 tallies)
+static AttenuateFn pick_warp_track_rec(int expm)
+{
+    switch (expm) {
+        case kExpPoly: return attenuate_warp_track_rec<kExpPoly>;
+        case kExpPolyWide: return attenuate_warp_track_rec<kExpPolyWide>;
+        case kExpMufu: return attenuate_warp_track_rec<kExpMufu>;
+        case kExpGlibc: return attenuate_warp_track_rec<kExpGlibc>;
+        case kExpTable: return attenuate_warp_track_rec<kExpTable>;
+    }
+    return nullptr;
+}
+
 // expm is the internal mode (kExpPolyWide resolved by the caller)
 static KernelChoice choose_kernel(const Shape &s, int math, int expm, bool f64, bool geom, bool a32)
 {
@@ -353,9 +366,12 @@ static int select_kernel(smk_ctx *c)
     const char *force64 = getenv("SMK_ADDR64");
     const bool a32 = (uint64_t)c->rows * c->shape.groups_pad * sizeof(float) < (1ull << 32) && !(force64 && force64[0] == '1');
     bool warp_track32 = false;
-    if (!fn && c->d_records) {
+    if (!fn && c->d_records && c->shape.groups_pad <= 32) {
         fn = pick_record(c->shape.groups_pad, c->rec_gpl, expm, f64, geom);
         family = c->rec_gpl == 2 ? "attenuate_record_tracks<2 groups/lane" : "attenuate_record_tracks<4 groups/lane";
+    } else if (!fn && c->d_records) {
+        fn = pick_warp_track_rec(expm);
+        family = "attenuate_warp_track_rec<2 groups/lane";
     }
     if (!fn) {
         const KernelChoice k = choose_kernel(c->shape, c->p.math_mode, expm, f64, geom, a32);
@@ -489,6 +505,16 @@ int smk_create(const smk_params *p, smk_ctx **out)
         if ((gpl == 2 || gpl == 4) && gpl != gpl_default && p->exp_mode != SMK_EXP_POLY) gpl = gpl_default;
         if (eligible && (gpl == 2 || gpl == 4)) {
             c->rec_gpl = gpl;
+            if (e == cudaSuccess) e = cudaMalloc(&c->d_records, slab * 4);
+        }
+        // 33..64 groups, one track per warp: the same records feed attenuate_warp_track_rec (SMK_WT_RECORDS=0 keeps the
+        // row arrays: A/B and the cross-check test)
+        const char *wt = getenv("SMK_WT_RECORDS");
+        const bool wt_eligible = shape.nchunk == 1 && shape.lpt == 16 && p->math_mode == kMathFast &&
+                                 !(p->flags & (SMK_FLAG_SEGMENT_GEOMETRY | SMK_FLAG_TALLY_F64)) && slab * 4 < (1ull << 32) &&
+                                 c->rows * 32 < (1ll << 30);
+        if (wt_eligible && !(wt && wt[0] == '0')) {
+            c->rec_gpl = 2;
             if (e == cudaSuccess) e = cudaMalloc(&c->d_records, slab * 4);
         }
     }
@@ -778,7 +804,7 @@ static int launch(smk_ctx *c, int64_t track_begin, int64_t track_end)
             build_records<4><<<layout_grid(c->rows * (Gp / 4)), 256, 0, c->stream>>>(c->d_source, c->d_sigT, c->d_records, c->rows, c->p.fine_axial_intervals, Gp);
         SMK_CUDA(cudaGetLastError());
         c->launches += 1;
-        lanes_per_track = Gp / c->rec_gpl;
+        lanes_per_track = Gp / c->rec_gpl;      // (32 for the one-track-per-warp shapes)
     }
 
     // persistent grid: a whole number of CTAs per SM; warps claim work items dynamically

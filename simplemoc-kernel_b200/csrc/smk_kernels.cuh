@@ -4,6 +4,8 @@
 //       attenuate_segment (/root/reference/src/cpu/kernel.c:43-55, 75-333), ONE WARP PER TRACK, FAST
 //       arithmetic.  GPL = energy groups per lane: 4 for 65..128 groups (128-bit loads, red.v4), 2 for
 //       33..64 groups (64-bit loads, red.v2).
+//   attenuate_warp_track_rec<EXPM>               33..64 groups, constant geometry: attenuate_warp_track<2> fed by one
+//       256-bit load per lane and segment from the same records
 //   attenuate_record_tracks<LPT, GPL, EXPM, F64, GEOM> <= 32 groups, FAST: sub-warp tracks fed by one or two
 //       256-bit loads per lane and segment from gather records (build_records)
 //   attenuate_tracks<LPT, NCHUNK, MATH, EXPM, GEOM> the general kernel: sub-warp tracks for <= 32 groups,
@@ -713,6 +715,86 @@ attenuate_record_tracks(const KernelArgs a)
 
         if (a.psi_out != nullptr && tvalid)
             reinterpret_cast<V *>(a.psi_out)[(track - a.track_begin) * LPT + sub] = psi;
+    }
+
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) checksum += __shfl_xor_sync(kFull, checksum, off);
+    if (lane == 0 && checksum != 0ull) atomicAdd(a.checksum, checksum);
+}
+
+// ------------------------------------------------------------------------------
+// attenuate_warp_track_rec<EXPM>: attenuate_warp_track<2> (33..64 groups: one track per warp, two groups per lane,
+// warp-uniform segment types, constant geometry, f32 tallies) fed from the gather records of build_records<2>: ONE
+// 256-bit load per lane and segment instead of a sigT load + 2-3 row loads of 64 bits, ONE shuffled word per segment
+// (the type flags ride above the row index), no sigT index and no neighbour-row addresses: 68 -> 61 instructions per
+// lane and segment.  Same typed bodies, same arithmetic: psi per track is bit-identical to attenuate_warp_track.
+// 64 groups 6.84e11 -> 7.24e11, config 4 6.91e11 -> 7.38e11 (profiles/ab_r02.md r02p).  At 65..128 groups (four
+// groups per lane) neither form pays: gather records move 11 % more bytes through a 4 x larger footprint (-10 %), and
+// interleaving the sigT row with every source row (same loads off one address, one shuffle) is within the noise
+// (r02q): that shape is bound by the FP32 pipe, not by its 25 non-FP instructions per segment.
+// ------------------------------------------------------------------------------
+template <int EXPM>
+__global__ void __launch_bounds__(kThreadsPerBlock, kMinBlocksHalf)
+attenuate_warp_track_rec(const KernelArgs a)
+{
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    constexpr int kWarps = kThreadsPerBlock / 32;
+    constexpr uint32_t ROWV = 32;
+
+    __shared__ float2 s_pairs[kTableReach];
+    if constexpr (EXPM == kExpTable) {
+        if (threadIdx.x < kTableReach) s_pairs[threadIdx.x] = c_exp_table.pairs[threadIdx.x];
+        __syncthreads();
+    }
+    int lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const int warp = threadIdx.x >> 5;
+    const int64_t warp_global = (int64_t)blockIdx.x * kWarps + warp;
+    const uint32_t F = (uint32_t)a.fai_count;
+    const int p = a.seg_per_track;
+    const char *const rec = reinterpret_cast<const char *>(a.records);
+    float *const tally = warp_tally(a, warp_global);
+    const int64_t n_tracks = a.track_end - a.track_begin;
+    unsigned long long checksum = 0ull;
+    const FitCoeffs fc = {};
+
+    for (int64_t w = claim_work(a, lane, 1); w < n_tracks; w = claim_work(a, lane, 1)) {
+        const int64_t track = a.track_begin + w;
+        const int64_t s0 = track * p;
+        const int64_t left = a.segments - s0;
+        const int nseg = left < p ? (int)left : p;
+
+        // incoming angular flux of the track (kernel.c:29-30): one Philox block covers 4 groups = two lanes
+        const u32x4 r0 = stream_words(a.keys, (uint64_t)track, (uint32_t)(lane >> 1), kDomainPsi);
+        float2 psi = (lane & 1) ? make_float2(u01(r0.z), u01(r0.w)) : make_float2(u01(r0.x), u01(r0.y));
+
+        for (int b = 0; b < nseg; b += 32) {
+            uint32_t my_pk = 0u;
+            if (b + lane < nseg) {
+                const uint64_t seg = (uint64_t)(s0 + b + lane);
+                const u32x4 r = stream_words(a.keys, seg, 0u, kDomainSegment);
+                const uint32_t qsr = fastmod(r.x >> 1, a.mod_regions);       // kernel.c:47
+                const uint32_t fai = fastmod(r.y >> 1, a.mod_fai);           // kernel.c:50
+                checksum += checksum_term(qsr, fai, F, seg);
+                // row * 32 < 2^30 (smk_create checks): the type flags ride in the two top bits
+                my_pk = ((qsr * F + fai) * ROWV) | (fai == 0u ? kSgFirst : 0u) | (fai == F - 1u ? kSgLast : 0u);
+            }
+            const int count = (nseg - b) < 32 ? (nseg - b) : 32;
+#pragma unroll kSegmentUnroll
+            for (int k = 0; k < count; ++k) {
+                const uint32_t pk = __shfl_sync(kFull, my_pk, k);
+                const uint32_t idx = (pk & ~(kSgFirst | kSgLast)) | (uint32_t)lane;
+                const Rec8 q = ldg256(ptr_add_index<true>(rec, idx * 32u));     // {sigT, y[FAI-1], y[FAI], y[FAI+1]}
+                float2 t;
+                if ((int32_t)pk < 0) attenuate_lane<EXPM, kFitFirst, false>(fc, q.b, q.c, q.d, q.a, s_pairs, psi, t);
+                else if (pk & kSgLast) attenuate_lane<EXPM, kFitLast, false>(fc, q.b, q.c, q.d, q.a, s_pairs, psi, t);
+                else attenuate_lane<EXPM, kFitInterior, false>(fc, q.b, q.c, q.d, q.a, s_pairs, psi, t);
+                tally_lane<false, true>(tally, nullptr, idx, t);                            // kernel.c:276
+            }
+        }
+
+        if (a.psi_out != nullptr)
+            reinterpret_cast<float2 *>(a.psi_out)[(track - a.track_begin) * ROWV + lane] = psi;
     }
 
 #pragma unroll
