@@ -503,7 +503,11 @@ int smk_create(const smk_params *p, smk_ctx **out)
                               c->rows * (shape.groups_pad / 2) < (1ll << 30);
         // the non-default record shape is compiled for the POLY exponential only
         if ((gpl == 2 || gpl == 4) && gpl != gpl_default && p->exp_mode != SMK_EXP_POLY) gpl = gpl_default;
-        if (eligible && (gpl == 2 || gpl == 4)) {
+        // the record kernels address with 32-bit byte offsets only: SMK_ADDR64=1 (plain 64-bit addressing forced, a test
+        // knob) keeps the row-array kernels
+        const char *force64 = getenv("SMK_ADDR64");
+        const bool plain64 = force64 && force64[0] == '1';
+        if (eligible && !plain64 && (gpl == 2 || gpl == 4)) {
             c->rec_gpl = gpl;
             if (e == cudaSuccess) e = cudaMalloc(&c->d_records, slab * 4);
         }
@@ -513,7 +517,7 @@ int smk_create(const smk_params *p, smk_ctx **out)
         const bool wt_eligible = shape.nchunk == 1 && shape.lpt == 16 && p->math_mode == kMathFast &&
                                  !(p->flags & (SMK_FLAG_SEGMENT_GEOMETRY | SMK_FLAG_TALLY_F64)) && slab * 4 < (1ull << 32) &&
                                  c->rows * 32 < (1ll << 30);
-        if (wt_eligible && !(wt && wt[0] == '0')) {
+        if (wt_eligible && !plain64 && !(wt && wt[0] == '0')) {
             c->rec_gpl = 2;
             if (e == cudaSuccess) e = cudaMalloc(&c->d_records, slab * 4);
         }

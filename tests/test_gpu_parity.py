@@ -512,6 +512,7 @@ def test_wide_and_32bit_address_forms_agree(smk, oracle, monkeypatch, G, geom):
     _, chk_want = oracle.run(src, want, sig, N, p, seed, nthreads=0, flags=GEOM if geom else 0,
                              geom7=geometry7(REFERENCE_GEOMETRY, 0.25) if geom else None)
     out = {}
+    monkeypatch.setenv("SMK_WT_RECORDS", "0")     # the row-array kernel has the two forms (the record kernels are 32-bit only)
     for force in ("0", "1"):
         monkeypatch.setenv("SMK_ADDR64", force)
         I = make_input(smk, R, F, G, N, p, seed, "poly", "fast", geom=g)
