@@ -445,8 +445,14 @@ attenuate_tracks(const KernelArgs a)
                     const uint32_t w3 = __shfl_sync(kFull, my_w3, k, LPT);
                     g = segment_geometry(a.geom, w2, w3);
                 }
-                FitCoeffs fc;
-                if constexpr (MATH == kMathFast) fc = GEOM ? fit_coeffs_geom(g, a.mesh, first, last) : fit_coeffs(first, last);
+                // LPT == 32 (blocks of 256 groups): one track per warp, so the segment type is warp-uniform and the
+                // statically typed bodies apply (edge bodies skip the quadratic terms: 29 instead of 45 operations)
+                constexpr bool kTyped = (LPT == 32);
+                FitCoeffs fc = {};
+                if constexpr (MATH == kMathFast) {
+                    if constexpr (kTyped) { if constexpr (GEOM) fc = fit_coeffs_geom_typed(g, a.mesh, first || last); }
+                    else fc = GEOM ? fit_coeffs_geom(g, a.mesh, first, last) : fit_coeffs(first, last);
+                }
 
 #pragma unroll
                 for (int c = 0; c < NCHUNK; ++c) {
@@ -456,7 +462,11 @@ attenuate_tracks(const KernelArgs a)
                     const float4 y1 = first ? zero : ldg4(src + c * LPT - row_f4);
                     const float4 y3 = last ? zero : ldg4(src + c * LPT + row_f4);
                     float4 t, ps = psi[c];
-                    if constexpr (MATH == kMathFast) {
+                    if constexpr (MATH == kMathFast && kTyped) {
+                        if (first) attenuate_lane<EXPM, kFitFirst, GEOM>(fc, y1, y2, y3, st, s_pairs, ps, t);
+                        else if (last) attenuate_lane<EXPM, kFitLast, GEOM>(fc, y1, y2, y3, st, s_pairs, ps, t);
+                        else attenuate_lane<EXPM, kFitInterior, GEOM>(fc, y1, y2, y3, st, s_pairs, ps, t);
+                    } else if constexpr (MATH == kMathFast) {
                         // tracks of different types share a warp -> per-lane coefficients
                         attenuate_lane<EXPM, kFitDynamic, GEOM>(fc, y1, y2, y3, st, s_pairs, ps, t);
                     } else {
