@@ -391,8 +391,13 @@ def e2e_run(torch, dist, smk, dev, rank, world, a, steps):
         st, ctx, t_tally, t_src, t_sig, Gp = lanes[k % 2]
         out = outs[k % 2]
         with torch.cuda.stream(st):
+            # (wait_finalized: the other lane's `flux0 + tallies` pass goes in front of this sweep -- a persistent grid
+            # that would otherwise starve it, its download and the next upload for a whole sweep, tools/e2e_timeline.py;
+            # the H2D copies above it still overlap the other lane's sweep)
+            other = lanes[(k + 1) % 2][1]
             if world == 1:
                 ctx.upload_async(src, flux0, sig)                  # H2D (also zeroes the tally deltas)
+                ctx.wait_finalized(other)
                 ctx.run_async(tb, te)
                 ctx.download_flux_rows_async(0, rows, out)         # D2H of flux0 + tallies
             else:
@@ -403,6 +408,7 @@ def e2e_run(torch, dist, smk, dev, rank, world, a, steps):
                 multi.gather_row_slices(t_sig, R, Gp, world)
                 ctx.set_sigt_bound(sig_bound)
                 ctx.reset_tallies()
+                ctx.wait_finalized(other)
                 ctx.run_async(tb, te)
                 if sliced:
                     multi.reduce_row_slices(t_tally, rows, Gp, world)

@@ -166,6 +166,14 @@ int   smk_download_flux(smk_ctx *ctx, float *fine_flux_out);
 /* rows [row_begin, row_begin + rows) of the same (out[rows][G]), enqueue only: for callers that
  * reduce-scatter the tallies over ranks and read back one slice per rank */
 int   smk_download_flux_rows_async(smk_ctx *ctx, int64_t row_begin, int64_t rows, float *out);
+/* Two contexts pipelined on ONE GPU (uploads / downloads of one under the sweep of the other): the sweep is a
+ * persistent grid that fills every SM, so a small kernel of the other context that becomes ready at the same moment
+ * (the `flux0 + tallies` pass in front of a download) can lose the race and wait a whole sweep for an SM, delaying
+ * the download, the caller's next upload and with it the sweep after.  smk_wait_finalized(ctx, other) makes
+ * everything enqueued on ctx from now on wait (on the device, cudaStreamWaitEvent) until the `flux0 + tallies` pass
+ * of `other`'s most recent smk_download_flux* has run; the copy itself still overlaps.  No-op if `other` has not
+ * enqueued a download yet.  Call it before smk_run_async. */
+int   smk_wait_finalized(smk_ctx *ctx, smk_ctx *other);
 /* outgoing psi of the tracks [track_begin, track_end) swept by the LAST smk_run*:
  * psi_out[(t - track_begin) * G + g]; n_tracks must equal track_end - track_begin of that run
  * (SMK_EINVAL otherwise: it is the capacity of psi_out); needs SMK_FLAG_KEEP_PSI */

@@ -92,7 +92,7 @@ ABI_SYMBOLS = (
     "smk_multi_device_count", "smk_multi_set_geometry",
     "smk_set_geometry", "smk_get_geometry", "smk_kernel_name", "smk_upload_async",
     "smk_upload_rows_async", "smk_scan_sigt_max", "smk_download_flux_rows_async",
-    "smk_debug_segment_geometry", "smk_set_sigt_bound",
+    "smk_debug_segment_geometry", "smk_set_sigt_bound", "smk_wait_finalized",
 )
 
 
@@ -130,6 +130,7 @@ def _load() -> C.CDLL:
     L.smk_scan_sigt_max.argtypes = [vp, C.POINTER(C.c_float)]
     L.smk_set_sigt_bound.argtypes = [vp, C.c_float]
     L.smk_download_flux_rows_async.argtypes = [vp, i64, i64, vp]
+    L.smk_wait_finalized.argtypes = [vp, vp]
     L.smk_multi_set_geometry.argtypes = [vp, C.POINTER(Geometry)]
     L.smk_debug_segment_geometry.argtypes = [C.POINTER(Params), C.POINTER(Geometry), i64, i64, _f32p]
     L.smk_download_checksum.argtypes = [vp, C.POINTER(C.c_uint64)]
@@ -294,6 +295,11 @@ class Context:
 
     def download_flux_rows_async(self, row_begin: int, rows: int, out):
         _check(lib.smk_download_flux_rows_async(self._h, row_begin, rows, self._ptr(out)))
+
+    def wait_finalized(self, other: "Context"):
+        """Everything enqueued on this context from now on waits (on the device) for the flux0 + tallies pass of
+        `other`'s last download: keeps that small kernel from starving behind this context's persistent sweep."""
+        _check(lib.smk_wait_finalized(self._h, other._h))
 
     def fill_device(self, sigt_floor: float = 0.0):
         _check(lib.smk_fill_device(self._h, sigt_floor))

@@ -277,6 +277,8 @@ struct smk_ctx {
     cudaStream_t stream;
     bool own_stream;
     cudaEvent_t ev0, ev1;
+    cudaEvent_t ev_finalized;    // recorded after the flux0 + tallies pass of the last download (smk_wait_finalized)
+    bool finalized_recorded;
     bool have_data;
     int64_t launches;
 };
@@ -466,6 +468,7 @@ int smk_create(const smk_params *p, smk_ctx **out)
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) { c->own_stream = true; e = cudaEventCreate(&c->ev0); }
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_finalized, cudaEventDisableTiming);
     cudaDeviceProp prop;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, p->device);
     if (e == cudaSuccess) c->sm_count = prop.multiProcessorCount;
@@ -564,6 +567,7 @@ void smk_destroy(smk_ctx *c)
     cudaFree(c->d_records);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_finalized) cudaEventDestroy(c->ev_finalized);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -874,7 +878,19 @@ int smk_download_flux_rows_async(smk_ctx *c, int64_t row_begin, int64_t rows, fl
                                                                    stage, rows, G, Gp, c->replicas, c->rows * Gp, scale);
     SMK_CUDA(cudaGetLastError());
     c->launches += 1;
+    SMK_CUDA(cudaEventRecord(c->ev_finalized, c->stream));
+    c->finalized_recorded = true;
     SMK_CUDA(cudaMemcpyAsync(out, stage, (size_t)rows * G * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    return SMK_OK;
+}
+
+int smk_wait_finalized(smk_ctx *c, smk_ctx *other)
+{
+    if (!c || !other) return fail(SMK_EINVAL, "NULL argument");
+    if (c == other || !other->finalized_recorded) return SMK_OK;     // stream order / nothing to wait for
+    if (c->p.device != other->p.device) return fail(SMK_EINVAL, "contexts on different devices (%d, %d)", c->p.device, other->p.device);
+    SMK_CUDA(cudaSetDevice(c->p.device));
+    SMK_CUDA(cudaStreamWaitEvent(c->stream, other->ev_finalized, 0));
     return SMK_OK;
 }
 

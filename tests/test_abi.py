@@ -125,6 +125,7 @@ def test_multi_and_misc_argument_validation(smk):
     assert smk.lib.smk_upload_async(None, None, None, None) == -1
     assert smk.lib.smk_upload_rows_async(None, 0, 0, 0, None) == -1
     assert smk.lib.smk_download_flux_rows_async(None, 0, 0, None) == -1
+    assert smk.lib.smk_wait_finalized(None, None) == -1
     assert smk.lib.smk_set_geometry(None, None) == -1
     assert smk.lib.smk_scan_sigt_max(None, None) == -1
     assert smk.lib.smk_kernel_name(None) == b""

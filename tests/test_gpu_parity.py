@@ -800,6 +800,42 @@ def test_row_range_upload_and_download(smk, oracle, G):
     assert l2rel(out.reshape(R, F, G), whole) <= TOL_STRICT
 
 
+def test_two_contexts_pipelined_with_wait_finalized(smk, oracle):
+    """Two contexts in flight on one GPU (the end-to-end loop of bench.py): smk_wait_finalized orders the other
+    context's flux0 + tallies pass in front of this context's sweep.  Pure scheduling: every step's flux is
+    bit-identical to the plain upload / run / download sequence (f64 tallies: order-independent sums)."""
+    import torch
+    R, F, G, N, p, seed = 120, 5, 128, 200_000, 100, 93
+    src, flux0, sig = oracle.fill(R, F, G, seed)
+    I = make_input(smk, R, F, G, N, p, seed, "poly", "fast", tally_f64=True)
+    want, _, chk = gpu_run(smk, I, src, flux0, sig)
+    lanes = []
+    for _ in range(2):
+        st = torch.cuda.Stream()
+        ctx = smk.Context(I)
+        ctx.set_stream(st.cuda_stream)
+        lanes.append((st, ctx, np.empty((R * F, G), np.float32)))
+    outs = []
+    for k in range(6):
+        st, ctx, out = lanes[k % 2]
+        st.synchronize()                               # the lane's previous result is on the host
+        if k >= 2:
+            outs.append(out.copy())
+        ctx.upload_async(src, flux0, sig)
+        ctx.wait_finalized(lanes[(k + 1) % 2][1])      # no-op for k = 0: nothing downloaded yet
+        ctx.wait_finalized(ctx)                        # a context never waits for itself
+        ctx.run_async()
+        ctx.download_flux_rows_async(0, R * F, out)
+    for st, ctx, out in lanes:
+        st.synchronize()
+        outs.append(out.copy())
+        assert ctx.checksum() == chk
+        ctx.close()
+    assert len(outs) == 6
+    for o in outs:
+        assert np.array_equal(bits(o.reshape(R, F, G)), bits(want))
+
+
 TUNING_LIB = os.path.join(ROOT, "simplemoc-kernel_b200", "lib", "libsmk_tuning.so")
 
 
