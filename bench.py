@@ -343,6 +343,11 @@ def run_leg(torch, dist, smk, dev, rank, world, flush, a, name, *, steps=3, warm
            "kernel": sw.ctx.kernel_name, "roofline": binding,
            ("compute_roofline" if hbm_resident else "hbm_algorithmic"): other,
            "clocks": {"sm_mhz": clocks["sm_mhz"], "reasons": clocks["reasons"]}}
+    # measured DRAM bytes of one launch of this leg's shape (ncu --set full of this round), where recorded
+    t = recorded_traffic({"config3_7_groups": "config3_7_groups", "config4_64_groups_14_regions": "config4_64_groups_14_regions",
+                          "hbm_resident_432000_regions": "hbm_resident"}.get(name, ""))
+    if t and world == 1:
+        binding["traffic"], binding["traffic_source"] = t["dram_bytes_per_launch"], t["source"]
     sw.close()
     return rec if rank == 0 else None
 
