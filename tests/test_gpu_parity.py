@@ -133,6 +133,9 @@ CASES = [
     (50,  5, 128, 30_000,  1000, 21),   # 1000 segments per track: 32 id batches per track in the 128-group kernel
     (10,  5, 1500, 3_000,  100, 22),    # > 1024 groups (the reference CPU path takes any -e, io.c:129-138): 6 blocks
     (6,   3, 2050, 2_000,  50,  23),    # 9 group blocks, 254 padded groups
+    (40,  2, 7,   20_000,  100, 24),    # record kernel, F = 2: every interval is an edge (no neighbour on one side)
+    (50,  5, 7,   3_000,   1,   25),    # record kernel, seg_per_track = 1: one-segment id batches
+    (40,  5, 50,  20_017,  33,  26),    # 33..64 groups from records, ragged last track, odd track length
 ]
 # few-row stress cases: the order of the fp32 additions alone moves the result by more than the gate
 DEEP = {3, 13}
@@ -715,7 +718,7 @@ def test_geometry_constant_point_reproduces_reference_goldens(smk, path):
         assert l2rel(flux, z["flux"]) <= TOL_FAST
 
 
-GEOM_CASES = [c for c in CASES if c[5] in (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 15, 18, 19, 20, 21, 23)]
+GEOM_CASES = [c for c in CASES if c[5] in (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 15, 18, 19, 20, 21, 23, 24, 25)]
 
 
 @pytest.mark.parametrize("R,F,G,N,p,seed", GEOM_CASES)
