@@ -501,7 +501,13 @@ int smk_create(const smk_params *p, smk_ctx **out)
         const int gpl_default = record_groups_per_lane(shape.groups_pad, (p->flags & SMK_FLAG_SEGMENT_GEOMETRY) != 0);
         int gpl = gpl_default;
         if (const char *r = getenv("SMK_RECORDS")) gpl = atoi(r);
-        const bool eligible = shape.nchunk == 1 && shape.groups_pad <= 32 && p->math_mode == kMathFast &&
+        // Records trade bytes for instructions (one 32-byte record per lane instead of 2.6 + 1 partial rows: 11 % more
+        // bytes per segment): a win while records + tallies live in the L2, a loss once the sweep is HBM-bound.
+        // (an explicit SMK_RECORDS=2|4 / SMK_WT_RECORDS=1 overrides this rule: measurements)
+        const char *wt = getenv("SMK_WT_RECORDS");
+        const bool forced = getenv("SMK_RECORDS") != nullptr || (wt && wt[0] == '1');
+        const bool l2_resident = forced || (e == cudaSuccess && (double)slab * 5.0 <= 0.75 * (double)prop.l2CacheSize);
+        const bool eligible = shape.nchunk == 1 && shape.groups_pad <= 32 && p->math_mode == kMathFast && l2_resident &&
                               slab * 4 < (1ull << 32) &&
                               c->rows * (shape.groups_pad / 2) < (1ll << 30);
         // the non-default record shape is compiled for the POLY exponential only
@@ -516,8 +522,7 @@ int smk_create(const smk_params *p, smk_ctx **out)
         }
         // 33..64 groups, one track per warp: the same records feed attenuate_warp_track_rec (SMK_WT_RECORDS=0 keeps the
         // row arrays: A/B and the cross-check test)
-        const char *wt = getenv("SMK_WT_RECORDS");
-        const bool wt_eligible = shape.nchunk == 1 && shape.lpt == 16 && p->math_mode == kMathFast &&
+        const bool wt_eligible = shape.nchunk == 1 && shape.lpt == 16 && p->math_mode == kMathFast && l2_resident &&
                                  !(p->flags & (SMK_FLAG_SEGMENT_GEOMETRY | SMK_FLAG_TALLY_F64)) && slab * 4 < (1ull << 32) &&
                                  c->rows * 32 < (1ll << 30);
         if (wt_eligible && !plain64 && !(wt && wt[0] == '0')) {
