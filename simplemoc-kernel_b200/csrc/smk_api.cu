@@ -298,6 +298,7 @@ static int smk_tuning_select(smk_ctx *c)
     else if (strcmp(variant, "prefetch") == 0) fn = pick_pf_exp<true, false, false>(c->p.exp_mode);
     else if (strcmp(variant, "defer") == 0) fn = pick_pf_exp<false, true, false>(c->p.exp_mode);
     else if (strcmp(variant, "l1pf") == 0) fn = pick_pf_exp<false, false, true>(c->p.exp_mode);
+    else if (strcmp(variant, "pipe") == 0) fn = pick_pipe_exp(c->p.exp_mode);
     else if (strcmp(variant, "staged2") == 0 || strcmp(variant, "staged3") == 0) {
         const int stages = variant[6] - '0';
         fn = stages == 2 ? pick_staged_exp<1, 2>(c->p.exp_mode) : pick_staged_exp<1, 3>(c->p.exp_mode);

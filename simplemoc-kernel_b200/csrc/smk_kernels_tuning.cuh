@@ -508,6 +508,126 @@ static AttenuateFn pick_pf_exp(int expm)
     return nullptr;
 }
 
+// ------------------------------------------------------------------------------
+// attenuate_warp_track_pipe<EXPM>: attenuate_warp_track<4> (65..128 groups, constant geometry, f32 tallies, 32-bit
+// offsets) with the rows of segment k+1 copied global -> shared by per-lane cp.async (SASS LDGSTS, no registers held,
+// no barrier: every lane copies and later reads only its own 16 bytes of each row) while segment k is computed.
+// Measured (profiles/ab_r02.md r02x): psi bit-identical, 7.01e11 vs 7.45e11 (-6 %): the one-track-per-warp kernel is not
+// bound by its load latency (32 resident warps cover it); the extra LDGSTS / LDS / DEPBAR instructions cost more.
+// ------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int EXPM>
+__global__ void __launch_bounds__(kThreadsPerBlock, kMinBlocksFast)
+attenuate_warp_track_pipe(const KernelArgs a)
+{
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    constexpr int kWarps = kThreadsPerBlock / 32;
+    constexpr uint32_t ROWV = 32;
+
+    __shared__ float2 s_pairs[kTableReach];
+    __shared__ float4 s_stage[kWarps][2][4][32];          // [warp][slot][sigT, y1, y2, y3][lane]
+    if constexpr (EXPM == kExpTable) {
+        if (threadIdx.x < kTableReach) s_pairs[threadIdx.x] = c_exp_table.pairs[threadIdx.x];
+        __syncthreads();
+    }
+    int lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const int warp = threadIdx.x >> 5;
+    const int64_t warp_global = (int64_t)blockIdx.x * kWarps + warp;
+    const uint32_t F = (uint32_t)a.fai_count;
+    const int p = a.seg_per_track;
+    float *const tally = warp_tally(a, warp_global);
+    const int64_t n_tracks = a.track_end - a.track_begin;
+    unsigned long long checksum = 0ull;
+    const FitCoeffs fc = {};
+    float4 *const stage = &s_stage[warp][0][0][lane];     // slot s, row r at stage[(s * 4 + r) * 32]
+
+    for (int64_t w = claim_work(a, lane, 1); w < n_tracks; w = claim_work(a, lane, 1)) {
+        const int64_t track = a.track_begin + w;
+        const int64_t s0 = track * p;
+        const int64_t left = a.segments - s0;
+        const int nseg = left < p ? (int)left : p;
+        const u32x4 r0 = stream_words(a.keys, (uint64_t)track, (uint32_t)lane, kDomainPsi);
+        float4 psi = make_float4(u01(r0.x), u01(r0.y), u01(r0.z), u01(r0.w));
+
+        for (int b = 0; b < nseg; b += 32) {
+            uint32_t my_pk = 0u, my_sg = 0u;
+            if (b + lane < nseg) {
+                const uint64_t seg = (uint64_t)(s0 + b + lane);
+                const u32x4 r = stream_words(a.keys, seg, 0u, kDomainSegment);
+                const uint32_t qsr = fastmod(r.x >> 1, a.mod_regions);       // kernel.c:47
+                const uint32_t fai = fastmod(r.y >> 1, a.mod_fai);           // kernel.c:50
+                checksum += checksum_term(qsr, fai, F, seg);
+                my_pk = (qsr * F + fai) * ROWV;
+                my_sg = (qsr * ROWV) | (fai == 0u ? kSgFirst : 0u) | (fai == F - 1u ? kSgLast : 0u);
+            }
+            const int count = (nseg - b) < 32 ? (nseg - b) : 32;
+            // copies of segment kk of the batch into slot kk & 1; returns its (idx, sg)
+            auto issue = [&](int kk, uint32_t &idx_out, uint32_t &sg_out) {
+                const uint32_t idx = __shfl_sync(kFull, my_pk, kk) | (uint32_t)lane;
+                const uint32_t sg = __shfl_sync(kFull, my_sg, kk);
+                const float4 *src = ptr_add_index<true>(a.source, idx);
+                float4 *dst = stage + (kk & 1) * 4 * 32;
+                cp_async16(dst, ptr_add_index<true>(a.sigT, (sg & ~(kSgFirst | kSgLast)) | (uint32_t)lane));
+                cp_async16(dst + 2 * 32, src);
+                if ((int32_t)sg >= 0) cp_async16(dst + 1 * 32, src - ROWV);          // not the first interval
+                if (!(sg & kSgLast)) cp_async16(dst + 3 * 32, src + ROWV);           // not the last interval
+                cp_async_commit();
+                idx_out = idx;
+                sg_out = sg;
+            };
+            uint32_t idx, sg, idx_next = 0u, sg_next = 0u;
+            issue(0, idx, sg);
+            for (int k = 0; k < count; ++k) {
+                if (k + 1 < count) {
+                    issue(k + 1, idx_next, sg_next);
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                const float4 *slot = stage + (k & 1) * 4 * 32;
+                const float4 st = slot[0], y2 = slot[2 * 32];
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 t;
+                if ((int32_t)sg < 0) {
+                    attenuate_lane<EXPM, kFitFirst, false>(fc, zero, y2, slot[3 * 32], st, s_pairs, psi, t);
+                } else if (sg & kSgLast) {
+                    attenuate_lane<EXPM, kFitLast, false>(fc, slot[1 * 32], y2, zero, st, s_pairs, psi, t);
+                } else {
+                    attenuate_lane<EXPM, kFitInterior, false>(fc, slot[1 * 32], y2, slot[3 * 32], st, s_pairs, psi, t);
+                }
+                tally_lane<false, true>(tally, nullptr, idx, t);                            // kernel.c:276
+                idx = idx_next;
+                sg = sg_next;
+            }
+        }
+
+        if (a.psi_out != nullptr)
+            reinterpret_cast<float4 *>(a.psi_out)[(track - a.track_begin) * ROWV + lane] = psi;
+    }
+
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) checksum += __shfl_xor_sync(kFull, checksum, off);
+    if (lane == 0 && checksum != 0ull) atomicAdd(a.checksum, checksum);
+}
+
+static AttenuateFn pick_pipe_exp(int expm)
+{
+    switch (expm) {
+        case kExpPoly: return attenuate_warp_track_pipe<kExpPoly>;
+        case kExpMufu: return attenuate_warp_track_pipe<kExpMufu>;
+    }
+    return nullptr;
+}
+
 }  // namespace smk
 
 struct smk_ctx;

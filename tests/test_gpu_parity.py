@@ -843,7 +843,7 @@ TUNING_LIB = os.path.join(ROOT, "simplemoc-kernel_b200", "lib", "libsmk_tuning.s
 
 
 @pytest.mark.skipif(not os.path.exists(TUNING_LIB), reason="tuning build absent (make -C simplemoc-kernel_b200 tuning)")
-@pytest.mark.parametrize("variant", ["oldflat", "prefetch", "defer", "l1pf", "staged2", "staged3"])
+@pytest.mark.parametrize("variant", ["oldflat", "prefetch", "defer", "l1pf", "staged2", "staged3", "pipe"])
 def test_tuning_variants_parity(oracle, variant, tmp_path):
     """The measured-and-rejected kernel variants (DESIGN.md section 5.3) live in a separate tuning build;
     each one still has to reproduce the oracle (a variant that computes something else measures nothing)."""
