@@ -219,15 +219,16 @@ static AttenuateFn pick_record(int groups_pad, int gpl, int expm, bool f64, bool
     return nullptr;
 }
 
-// 33..64 groups: one track per warp from gather records (constant geometry, f32 tallies)
+// 33..64 groups: one track per warp from gather records (f32 tallies)
+template <bool GEOM>
 static AttenuateFn pick_warp_track_rec(int expm)
 {
     switch (expm) {
-        case kExpPoly: return attenuate_warp_track_rec<kExpPoly>;
-        case kExpPolyWide: return attenuate_warp_track_rec<kExpPolyWide>;
-        case kExpMufu: return attenuate_warp_track_rec<kExpMufu>;
-        case kExpGlibc: return attenuate_warp_track_rec<kExpGlibc>;
-        case kExpTable: return attenuate_warp_track_rec<kExpTable>;
+        case kExpPoly: return attenuate_warp_track_rec<kExpPoly, GEOM>;
+        case kExpPolyWide: return attenuate_warp_track_rec<kExpPolyWide, GEOM>;
+        case kExpMufu: return attenuate_warp_track_rec<kExpMufu, GEOM>;
+        case kExpGlibc: return attenuate_warp_track_rec<kExpGlibc, GEOM>;
+        case kExpTable: return attenuate_warp_track_rec<kExpTable, GEOM>;
     }
     return nullptr;
 }
@@ -373,7 +374,7 @@ static int select_kernel(smk_ctx *c)
         fn = pick_record(c->shape.groups_pad, c->rec_gpl, expm, f64, geom);
         family = c->rec_gpl == 2 ? "attenuate_record_tracks<2 groups/lane" : "attenuate_record_tracks<4 groups/lane";
     } else if (!fn && c->d_records) {
-        fn = pick_warp_track_rec(expm);
+        fn = geom ? pick_warp_track_rec<true>(expm) : pick_warp_track_rec<false>(expm);
         family = "attenuate_warp_track_rec<2 groups/lane";
     }
     if (!fn) {
@@ -524,7 +525,7 @@ int smk_create(const smk_params *p, smk_ctx **out)
         // 33..64 groups, one track per warp: the same records feed attenuate_warp_track_rec (SMK_WT_RECORDS=0 keeps the
         // row arrays: A/B and the cross-check test)
         const bool wt_eligible = shape.nchunk == 1 && shape.lpt == 16 && p->math_mode == kMathFast && l2_resident &&
-                                 !(p->flags & (SMK_FLAG_SEGMENT_GEOMETRY | SMK_FLAG_TALLY_F64)) && slab * 4 < (1ull << 32) &&
+                                 !(p->flags & SMK_FLAG_TALLY_F64) && slab * 4 < (1ull << 32) &&
                                  c->rows * 32 < (1ll << 30);
         if (wt_eligible && !plain64 && !(wt && wt[0] == '0')) {
             c->rec_gpl = 2;

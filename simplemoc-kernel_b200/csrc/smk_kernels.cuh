@@ -4,7 +4,7 @@
 //       attenuate_segment (/root/reference/src/cpu/kernel.c:43-55, 75-333), ONE WARP PER TRACK, FAST
 //       arithmetic.  GPL = energy groups per lane: 4 for 65..128 groups (128-bit loads, red.v4), 2 for
 //       33..64 groups (64-bit loads, red.v2).
-//   attenuate_warp_track_rec<EXPM>               33..64 groups, constant geometry: attenuate_warp_track<2> fed by one
+//   attenuate_warp_track_rec<EXPM, GEOM>         33..64 groups: attenuate_warp_track<2> fed by one
 //       256-bit load per lane and segment from the same records
 //   attenuate_record_tracks<LPT, GPL, EXPM, F64, GEOM> <= 32 groups, FAST: sub-warp tracks fed by one or two
 //       256-bit loads per lane and segment from gather records (build_records)
@@ -733,8 +733,8 @@ attenuate_record_tracks(const KernelArgs a)
 }
 
 // ------------------------------------------------------------------------------
-// attenuate_warp_track_rec<EXPM>: attenuate_warp_track<2> (33..64 groups: one track per warp, two groups per lane,
-// warp-uniform segment types, constant geometry, f32 tallies) fed from the gather records of build_records<2>: ONE
+// attenuate_warp_track_rec<EXPM, GEOM>: attenuate_warp_track<2> (33..64 groups: one track per warp, two groups per lane,
+// warp-uniform segment types, f32 tallies) fed from the gather records of build_records<2>: ONE
 // 256-bit load per lane and segment instead of a sigT load + 2-3 row loads of 64 bits, ONE shuffled word per segment
 // (the type flags ride above the row index), no sigT index and no neighbour-row addresses: 68 -> 61 instructions per
 // lane and segment.  Same typed bodies, same arithmetic: psi per track is bit-identical to attenuate_warp_track.
@@ -743,8 +743,8 @@ attenuate_record_tracks(const KernelArgs a)
 // interleaving the sigT row with every source row (same loads off one address, one shuffle) is within the noise
 // (r02q): that shape is bound by the FP32 pipe, not by its 25 non-FP instructions per segment.
 // ------------------------------------------------------------------------------
-template <int EXPM>
-__global__ void __launch_bounds__(kThreadsPerBlock, kMinBlocksHalf)
+template <int EXPM, bool GEOM>
+__global__ void __launch_bounds__(kThreadsPerBlock, GEOM ? kMinBlocksGeom : kMinBlocksHalf)
 attenuate_warp_track_rec(const KernelArgs a)
 {
     constexpr unsigned kFull = 0xFFFFFFFFu;
@@ -752,6 +752,8 @@ attenuate_warp_track_rec(const KernelArgs a)
     constexpr uint32_t ROWV = 32;
 
     __shared__ float2 s_pairs[kTableReach];
+    // GEOM: per warp, per segment of the batch: {ds, weight, q0_d, q0_s} {q1_d, q1_s, q2_s, -} (as attenuate_warp_track)
+    __shared__ float4 s_coef[GEOM ? kWarps : 1][GEOM ? 32 : 1][2];
     if constexpr (EXPM == kExpTable) {
         if (threadIdx.x < kTableReach) s_pairs[threadIdx.x] = c_exp_table.pairs[threadIdx.x];
         __syncthreads();
@@ -766,7 +768,6 @@ attenuate_warp_track_rec(const KernelArgs a)
     float *const tally = warp_tally(a, warp_global);
     const int64_t n_tracks = a.track_end - a.track_begin;
     unsigned long long checksum = 0ull;
-    const FitCoeffs fc = {};
 
     for (int64_t w = claim_work(a, lane, 1); w < n_tracks; w = claim_work(a, lane, 1)) {
         const int64_t track = a.track_begin + w;
@@ -788,19 +789,33 @@ attenuate_warp_track_rec(const KernelArgs a)
                 checksum += checksum_term(qsr, fai, F, seg);
                 // row * 32 < 2^30 (smk_create checks): the type flags ride in the two top bits
                 my_pk = ((qsr * F + fai) * ROWV) | (fai == 0u ? kSgFirst : 0u) | (fai == F - 1u ? kSgLast : 0u);
+                if constexpr (GEOM) {
+                    const SegGeometry g = segment_geometry(a.geom, r.z, r.w);
+                    const FitCoeffs f = fit_coeffs_geom_typed(g, a.mesh, fai == 0u || fai == F - 1u);
+                    s_coef[warp][lane][0] = make_float4(f.ds, f.weight, f.q0_d, f.q0_s);
+                    s_coef[warp][lane][1] = make_float4(f.q1_d, f.q1_s, f.q2_s, 0.0f);
+                }
             }
+            if constexpr (GEOM) __syncwarp();
             const int count = (nseg - b) < 32 ? (nseg - b) : 32;
 #pragma unroll kSegmentUnroll
             for (int k = 0; k < count; ++k) {
                 const uint32_t pk = __shfl_sync(kFull, my_pk, k);
                 const uint32_t idx = (pk & ~(kSgFirst | kSgLast)) | (uint32_t)lane;
                 const Rec8 q = ldg256(ptr_add_index<true>(rec, idx * 32u));     // {sigT, y[FAI-1], y[FAI], y[FAI+1]}
+                FitCoeffs fc = {};
+                if constexpr (GEOM) {
+                    const float4 c0 = s_coef[warp][k][0], c1 = s_coef[warp][k][1];
+                    fc.ds = c0.x; fc.weight = c0.y; fc.q0_d = c0.z; fc.q0_s = c0.w;
+                    fc.q1_d = c1.x; fc.q1_s = c1.y; fc.q2_s = c1.z;
+                }
                 float2 t;
-                if ((int32_t)pk < 0) attenuate_lane<EXPM, kFitFirst, false>(fc, q.b, q.c, q.d, q.a, s_pairs, psi, t);
-                else if (pk & kSgLast) attenuate_lane<EXPM, kFitLast, false>(fc, q.b, q.c, q.d, q.a, s_pairs, psi, t);
-                else attenuate_lane<EXPM, kFitInterior, false>(fc, q.b, q.c, q.d, q.a, s_pairs, psi, t);
+                if ((int32_t)pk < 0) attenuate_lane<EXPM, kFitFirst, GEOM>(fc, q.b, q.c, q.d, q.a, s_pairs, psi, t);
+                else if (pk & kSgLast) attenuate_lane<EXPM, kFitLast, GEOM>(fc, q.b, q.c, q.d, q.a, s_pairs, psi, t);
+                else attenuate_lane<EXPM, kFitInterior, GEOM>(fc, q.b, q.c, q.d, q.a, s_pairs, psi, t);
                 tally_lane<false, true>(tally, nullptr, idx, t);                            // kernel.c:276
             }
+            if constexpr (GEOM) __syncwarp();       // everyone is done with s_coef before the next batch overwrites it
         }
 
         if (a.psi_out != nullptr)

@@ -624,6 +624,30 @@ def test_warp_track_record_kernel_matches_row_kernel(smk, oracle, monkeypatch, G
     assert np.array_equal(bits(out["0"][1]), bits(out["1"][1]))
 
 
+@pytest.mark.parametrize("G,N,p", [(64, 40_033, 70), (40, 30_000, 100)])
+def test_warp_track_record_kernel_per_segment_geometry(smk, oracle, monkeypatch, G, N, p):
+    """33..64 groups with per-segment geometry: records against row arrays, psi bit for bit, flux within the gate of
+    the parametrised oracle."""
+    R, F, seed = 60, 5, 89
+    g7 = geometry7(REFERENCE_GEOMETRY, 0.25)
+    src, flux0, sig = oracle.fill(R, F, G, seed)
+    want = flux0.copy()
+    _, chk_want = oracle.run(src, want, sig, N, p, seed, nthreads=0, flags=GEOM, geom7=g7)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SMK_WT_RECORDS", mode)
+        I = make_input(smk, R, F, G, N, p, seed, "poly", "fast", geom=(REFERENCE_GEOMETRY, 0.25))
+        with smk.Context(I, keep_psi=True) as ctx:
+            ctx.upload(src, flux0, sig)
+            name = ctx.kernel_name
+            ctx.run()
+            out[mode] = (ctx.download_flux(), ctx.download_psi(ctx.n_tracks), ctx.checksum())
+        assert ("attenuate_warp_track_rec" in name) == (mode == "1") and "per-segment" in name, name
+        assert out[mode][2] == chk_want
+        assert l2rel(out[mode][0], want) <= TOL_FAST
+    assert np.array_equal(bits(out["0"][1]), bits(out["1"][1]))
+
+
 @pytest.mark.parametrize("exp_mode", ["mufu", "glibc", "table"])
 def test_record_kernel_other_exponentials_and_f64_tallies(smk, oracle, monkeypatch, exp_mode):
     """Every exponential of the record kernel against the general kernel: psi bit-identical, and with the f64 tally
