@@ -507,7 +507,7 @@ int smk_create(const smk_params *p, smk_ctx **out)
         // bytes per segment): a win while records + tallies live in the L2, a loss once the sweep is HBM-bound.
         // (an explicit SMK_RECORDS=2|4 / SMK_WT_RECORDS=1 overrides this rule: measurements)
         const char *wt = getenv("SMK_WT_RECORDS");
-        const bool forced = getenv("SMK_RECORDS") != nullptr || (wt && wt[0] == '1');
+        const bool forced = (getenv("SMK_RECORDS") && (gpl == 2 || gpl == 4)) || (wt && wt[0] == '1');
         const bool l2_resident = forced || (e == cudaSuccess && (double)slab * 5.0 <= 0.75 * (double)prop.l2CacheSize);
         const bool eligible = shape.nchunk == 1 && shape.groups_pad <= 32 && p->math_mode == kMathFast && l2_resident &&
                               slab * 4 < (1ull << 32) &&
