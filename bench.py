@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument("--exp", default="poly", choices=["poly", "mufu", "glibc", "table"])
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
     ap.add_argument("--geometry", action="store_true", help="per-segment geometry (SMK_FLAG_SEGMENT_GEOMETRY)")
+    ap.add_argument("--fit-per-sweep", action="store_true",
+                    help="SMK_FLAG_FIT_PER_SWEEP: the axial source fit once per (region, interval, group) per sweep "
+                         "instead of once per segment (off by default, as in the reference; <= 64 groups)")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-legs", action="store_true", help="skip the extra per-config legs / sub-records")
@@ -98,6 +101,7 @@ def config_dict(a):
     return {"workload": workload_name(a.egroups, a.segments, a.regions_2d, a.seg_per_track, a.gpus, a.geometry),
             "segments_global": a.segments, "egroups": a.egroups, "regions_2d": a.regions_2d,
             "seg_per_track": a.seg_per_track, "exp_mode": a.exp, "math_mode": a.math, "seed": a.seed,
+            "fit_per_sweep": bool(getattr(a, "fit_per_sweep", False)),
             "l2": "flushed between steps (256 MB memset); within a step the 38 MB working set of the "
                   "reference's default geometry is L2-resident by construction of the workload",
             "sharding": (f"tracks split over {a.gpus} ranks by contiguous range; one all-reduce of tally deltas per step"
@@ -226,29 +230,33 @@ def main_reference(a):
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
-def lane_ops_per_intersection(smk, egroups, F, geometry):
+def lane_ops_per_intersection(smk, egroups, F, geometry, fit_per_sweep=False):
     """FP32 lane-operations of the FAST/POLY arithmetic (csrc/smk_math.cuh, counted in the SASS of the
     default kernels: FFMA2 + FMUL2 + FADD2 per pair of groups): 45 per interior and 29 per edge
     intersection where the segment type is warp-uniform (33..128 groups: one track per warp), 45 for every
     intersection where tracks of different types share a warp (<= 32 groups) or rows are swept in blocks;
-    one more with per-segment geometry (the weight is applied per intersection instead of once at the end)."""
+    one more with per-segment geometry (the weight is applied per intersection instead of once at the end).
+    With --fit-per-sweep (SMK_FLAG_FIT_PER_SWEEP, <= 64 groups) the fit's 8 (interior) / 3 (edge) operations are
+    evaluated per (region, interval, group) and sweep instead: 37 / 26 remain in the segment loop."""
     extra = 1.0 if geometry else 0.0
     gp = smk.lib.smk_padded_groups(egroups)
-    if gp in (64, 128):
-        return ((45.0 + extra) * (F - 2) + (29.0 + extra) * 2) / F
-    return 45.0 + extra
+    hoist = fit_per_sweep and gp <= 64 and not geometry
+    interior, edge = (37.0, 26.0) if hoist else (45.0, 29.0)
+    if gp >= 64:
+        return ((interior + extra) * (F - 2) + (edge + extra) * 2) / F
+    return interior + extra
 
 
 class Sweep:
     """One device-resident problem on this rank + the timed sweep loop."""
 
     def __init__(self, torch, dist, smk, dev, rank, world, *, egroups, segments, regions_2d, seg_per_track, seed,
-                 exp, math, geometry=False):
+                 exp, math, geometry=False, fit_per_sweep=False):
         self.torch, self.dist, self.smk, self.dev, self.rank, self.world = torch, dist, smk, dev, rank, world
         self.G = egroups
         self.I = smk.Input(source_2D_regions=regions_2d, segments=segments, egroups=egroups,
                            seg_per_thread=seg_per_track, seed=seed, exp_mode=exp, math_mode=math,
-                           device=dev.index, segment_geometry=geometry).finalize()
+                           device=dev.index, segment_geometry=geometry, fit_per_sweep=fit_per_sweep).finalize()
         self.ctx = smk.Context(self.I)
         self.stream = torch.cuda.current_stream(dev)
         self.ctx.set_stream(self.stream.cuda_stream)
@@ -309,7 +317,7 @@ class Sweep:
         inter = float(self.my_segments) * self.G
         sec = kernel_ms_per_step * 1e-3
         algo_gbs = ALGO_BYTES_PER_INTERSECTION * inter / sec / 1e9
-        lane_ops = lane_ops_per_intersection(self.smk, self.G, F, self.I.segment_geometry)
+        lane_ops = lane_ops_per_intersection(self.smk, self.G, F, self.I.segment_geometry, self.I.fit_per_sweep)
         sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
         sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
         fp32_peak = sms * 128 * sm_mhz * 1e6
@@ -329,7 +337,7 @@ class Sweep:
 def run_leg(torch, dist, smk, dev, rank, world, flush, a, name, *, steps=3, warmup=3, hbm_resident=False, **kw):
     """One short timed leg for another configuration; returns its record (rank 0) or None."""
     base = dict(egroups=128, segments=100_000_000 * world, regions_2d=5000, seg_per_track=a.seg_per_track,
-                seed=a.seed, exp=a.exp, math=a.math, geometry=False)
+                seed=a.seed, exp=a.exp, math=a.math, geometry=False, fit_per_sweep=False)
     base.update(kw)
     sw = Sweep(torch, dist, smk, dev, rank, world, **base)
     sampler = ClockSampler(dev.index)
@@ -340,6 +348,9 @@ def run_leg(torch, dist, smk, dev, rank, world, flush, a, name, *, steps=3, warm
     rec = {"name": name, "workload": workload_name(sw.G, sw.I.segments, base["regions_2d"], base["seg_per_track"],
                                                    world, base["geometry"]),
            "value": value, "unit": UNIT, "ms_per_step": total_ms / steps, "steps": steps, "warmup": warmup,
+           "arithmetic": ("source fit evaluated once per (region, interval, group) per sweep (SMK_FLAG_FIT_PER_SWEEP): "
+                          "NOT the reference's per-segment evaluation; results bit-identical" if base["fit_per_sweep"]
+                          else "as the reference: every operation of attenuate_segment per segment"),
            "kernel": sw.ctx.kernel_name, "roofline": binding,
            ("compute_roofline" if hbm_resident else "hbm_algorithmic"): other,
            "clocks": {"sm_mhz": clocks["sm_mhz"], "reasons": clocks["reasons"]}}
@@ -527,7 +538,8 @@ def main_ours(a):
 
     # ---- the headline sweep ---------------------------------------------------------------------
     main = Sweep(torch, dist, smk, dev, rank, world, egroups=G, segments=a.segments, regions_2d=a.regions_2d,
-                 seg_per_track=a.seg_per_track, seed=a.seed, exp=a.exp, math=a.math, geometry=a.geometry)
+                 seg_per_track=a.seg_per_track, seed=a.seed, exp=a.exp, math=a.math, geometry=a.geometry,
+                 fit_per_sweep=a.fit_per_sweep)
     sampler = ClockSampler(local_rank)
     total_ms, kernel_total_ms, launches = main.timed(a.steps, a.warmup, flush, sampler)
     clocks = sampler.stop()
@@ -556,6 +568,9 @@ def main_ours(a):
                          ("config4_64_groups_14_regions", dict(egroups=64, regions_2d=10)),
                          ("hbm_resident_432000_regions", dict(regions_2d=320000, hbm_resident=True)),
                          ("config2_per_segment_geometry", dict(geometry=True)),
+                         # NOT the default arithmetic: the source fit hoisted out of the segment loop (same results)
+                         ("config3_7_groups_fit_per_sweep", dict(egroups=7, fit_per_sweep=True)),
+                         ("config4_64_groups_14_regions_fit_per_sweep", dict(egroups=64, regions_2d=10, fit_per_sweep=True)),
                          ("config5_1e10_segments_one_gpu", dict(segments=CONFIG5_SEGMENTS, steps=1, warmup=1))):
             legs.append(run_leg(torch, dist, smk, dev, rank, world, flush, a, name, **kw))
     nccl_flux = None

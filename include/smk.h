@@ -86,6 +86,15 @@ typedef struct smk_params {
                                        yardstick for fp32 accumulation noise); every kernel */
 #define SMK_FLAG_SEGMENT_GEOMETRY 4 /* dz, zin, weight, mu, mu2, ds of kernel.c:99-104 vary per segment
                                        (smk_geometry / smk_set_geometry below)  */
+#define SMK_FLAG_FIT_PER_SWEEP 8     /* OFF by default.  The quadratic axial source fit (kernel.c:111-191) depends only
+                                       on (region, interval, group): with this flag it is evaluated once per sweep for
+                                       every such triple (inside smk_run*, by the pass that lays out the gather records)
+                                       instead of once per segment, with the same operations in the same order: results
+                                       are bit-identical, 8 of 45 operations per interior intersection leave the segment
+                                       loop.  The reference evaluates the fit per segment, so the default does too;
+                                       needs SMK_MATH_FAST and the constant geometry (SMK_EINVAL otherwise), and takes
+                                       effect for the shapes that sweep from gather records (<= 64 groups, working set
+                                       within the L2) -- smk_kernel_name says which form runs. */
 
 /*
  * Segment geometry.  /root/reference/src/cpu/kernel.c:95-104: "Some placeholder constants - In the

@@ -33,6 +33,7 @@ MATH_FAST, MATH_STRICT = 0, 1
 FLAG_KEEP_PSI = 1
 FLAG_TALLY_F64 = 2
 FLAG_SEGMENT_GEOMETRY = 4
+FLAG_FIT_PER_SWEEP = 8
 ARRAY_SOURCE, ARRAY_FLUX, ARRAY_SIGT = 0, 1, 2
 DEBUG_EXP_PACKED, DEBUG_EXP_WIDE, DEBUG_EXP_TRACK = 0x100, 0x200, 0x400
 # kernel.c:99-104: dz, zin, weight, mu, mu2, ds
@@ -193,6 +194,9 @@ class Input:
     tally_f64: bool = False              # diagnostic: f64 tally accumulators (SMK_FLAG_TALLY_F64)
     # per-segment geometry (SMK_FLAG_SEGMENT_GEOMETRY): kernel.c:99-104 as base values + spread
     segment_geometry: bool = False
+    # OFF by default: evaluate the axial source fit once per (region, interval, group) per sweep instead of once per
+    # segment (SMK_FLAG_FIT_PER_SWEEP; identical results, fewer operations in the segment loop; <= 64 groups)
+    fit_per_sweep: bool = False
     geometry: tuple = REFERENCE_GEOMETRY
     geometry_spread: float = 0.25
 
@@ -213,6 +217,8 @@ class Input:
             flags |= FLAG_TALLY_F64
         if self.segment_geometry:
             flags |= FLAG_SEGMENT_GEOMETRY
+        if self.fit_per_sweep:
+            flags |= FLAG_FIT_PER_SWEEP
         return Params(self.source_3D_regions, self.fine_axial_intervals, self.egroups,
                       self.seg_per_thread, self.segments, self.seed, EXP_MODES[self.exp_mode],
                       MATH_MODES[self.math_mode], self.device, flags)

@@ -185,6 +185,39 @@ static AttenuateFn pick_record_exp(int expm)
     return nullptr;
 }
 
+// SMK_FLAG_FIT_PER_SWEEP: records holding the fitted coefficients (the library's shapes, constant geometry)
+template <int LPT, int GPL, bool F64>
+static AttenuateFn pick_record_hoist(int expm)
+{
+    switch (expm) {
+        case kExpPoly: return attenuate_record_tracks<LPT, GPL, kExpPoly, F64, false, true>;
+        case kExpPolyWide: return attenuate_record_tracks<LPT, GPL, kExpPolyWide, F64, false, true>;
+        case kExpMufu: return attenuate_record_tracks<LPT, GPL, kExpMufu, F64, false, true>;
+    }
+    return nullptr;
+}
+
+static AttenuateFn pick_record_hoist(int groups_pad, int gpl, int expm, bool f64)
+{
+    switch (groups_pad * 10 + gpl) {
+        case 42: return f64 ? pick_record_hoist<2, 2, true>(expm) : pick_record_hoist<2, 2, false>(expm);
+        case 84: return f64 ? pick_record_hoist<2, 4, true>(expm) : pick_record_hoist<2, 4, false>(expm);
+        case 164: return f64 ? pick_record_hoist<4, 4, true>(expm) : pick_record_hoist<4, 4, false>(expm);
+        case 324: return f64 ? pick_record_hoist<8, 4, true>(expm) : pick_record_hoist<8, 4, false>(expm);
+    }
+    return nullptr;
+}
+
+static AttenuateFn pick_warp_track_rec_hoist(int expm)
+{
+    switch (expm) {
+        case kExpPoly: return attenuate_warp_track_rec<kExpPoly, false, true>;
+        case kExpPolyWide: return attenuate_warp_track_rec<kExpPolyWide, false, true>;
+        case kExpMufu: return attenuate_warp_track_rec<kExpMufu, false, true>;
+    }
+    return nullptr;
+}
+
 // ALL = every exponential (the shapes the library uses, record_groups_per_lane); otherwise POLY only: the other record
 // shape of each group count exists for the A/B knob SMK_RECORDS and the cross-check test
 template <int LPT, int GPL, bool F64, bool GEOM, bool ALL>
@@ -274,6 +307,7 @@ struct smk_ctx {
     double *d_tally64;           // SMK_FLAG_TALLY_F64: f64 tally accumulators, [R][F][G_pad]
     float *d_records;            // gather records of attenuate_record_tracks, [R*F][G_pad/2][8]; nullptr = not used
     int rec_gpl;                 // groups per lane of the record kernel (2 or 4)
+    bool hoist;                  // the selected kernel reads fitted records (SMK_FLAG_FIT_PER_SWEEP)
     float sigt_max;              // max(sigT) of the device data, +inf when unknown (partial uploads)
     cudaStream_t stream;
     bool own_stream;
@@ -325,8 +359,11 @@ static int validate(const smk_params *p, Shape &shape)
         return fail(SMK_EINVAL, "unknown exp_mode %d", p->exp_mode);
     if (p->math_mode != SMK_MATH_FAST && p->math_mode != SMK_MATH_STRICT)
         return fail(SMK_EINVAL, "unknown math_mode %d", p->math_mode);
-    if (p->flags & ~(SMK_FLAG_KEEP_PSI | SMK_FLAG_TALLY_F64 | SMK_FLAG_SEGMENT_GEOMETRY))
+    if (p->flags & ~(SMK_FLAG_KEEP_PSI | SMK_FLAG_TALLY_F64 | SMK_FLAG_SEGMENT_GEOMETRY | SMK_FLAG_FIT_PER_SWEEP))
         return fail(SMK_EINVAL, "unknown flag bits %#x", p->flags);
+    if ((p->flags & SMK_FLAG_FIT_PER_SWEEP) && (p->math_mode != SMK_MATH_FAST || (p->flags & SMK_FLAG_SEGMENT_GEOMETRY)))
+        return fail(SMK_EINVAL, "SMK_FLAG_FIT_PER_SWEEP needs SMK_MATH_FAST and the constant geometry (the fit is only "
+                                "sweep-invariant there; STRICT is the reference's own per-segment arithmetic)");
     if (!shape_for(p->egroups, shape)) return fail(SMK_EINVAL, "egroups = %d unsupported", p->egroups);
     if ((int64_t)p->source_3D_regions * p->fine_axial_intervals * (shape.groups_pad / 4) >= (1ll << 31))
         return fail(SMK_EINVAL, "regions * intervals * padded groups / 4 must be < 2^31 (32-bit row offsets)");
@@ -370,11 +407,17 @@ static int select_kernel(smk_ctx *c)
     const char *force64 = getenv("SMK_ADDR64");
     const bool a32 = (uint64_t)c->rows * c->shape.groups_pad * sizeof(float) < (1ull << 32) && !(force64 && force64[0] == '1');
     bool warp_track32 = false;
+    c->hoist = false;
+    const bool want_hoist = (c->p.flags & SMK_FLAG_FIT_PER_SWEEP) != 0;
     if (!fn && c->d_records && c->shape.groups_pad <= 32) {
-        fn = pick_record(c->shape.groups_pad, c->rec_gpl, expm, f64, geom);
+        if (want_hoist) fn = pick_record_hoist(c->shape.groups_pad, c->rec_gpl, expm, f64);
+        c->hoist = fn != nullptr;
+        if (!fn) fn = pick_record(c->shape.groups_pad, c->rec_gpl, expm, f64, geom);
         family = c->rec_gpl == 2 ? "attenuate_record_tracks<2 groups/lane" : "attenuate_record_tracks<4 groups/lane";
     } else if (!fn && c->d_records) {
-        fn = geom ? pick_warp_track_rec<true>(expm) : pick_warp_track_rec<false>(expm);
+        if (want_hoist) fn = pick_warp_track_rec_hoist(expm);
+        c->hoist = fn != nullptr;
+        if (!fn) fn = geom ? pick_warp_track_rec<true>(expm) : pick_warp_track_rec<false>(expm);
         family = "attenuate_warp_track_rec<2 groups/lane";
     }
     if (!fn) {
@@ -392,9 +435,9 @@ static int select_kernel(smk_ctx *c)
         if (c->blocks_per_sm < 1) c->blocks_per_sm = 1;
     }
     c->exp_internal = expm;
-    snprintf(c->kernel_name, sizeof c->kernel_name, "%s, %s, %s, %s tally, %s geometry%s>", family,
+    snprintf(c->kernel_name, sizeof c->kernel_name, "%s, %s, %s, %s tally, %s geometry%s%s>", family,
              c->p.math_mode == kMathStrict ? "strict" : "fast", exp_name[expm], f64 ? "f64" : "f32",
-             geom ? "per-segment" : "const", warp_track32 ? ", 32-bit offsets" : "");
+             geom ? "per-segment" : "const", warp_track32 ? ", 32-bit offsets" : "", c->hoist ? ", fit per sweep" : "");
     return SMK_OK;
 }
 
@@ -813,10 +856,18 @@ static int launch(smk_ctx *c, int64_t track_begin, int64_t track_end)
         // derived layout, rebuilt from the canonical rows inside every sweep (they may have been written through
         // any of the upload paths or directly on the device since the last one)
         const int Gp = c->shape.groups_pad;
-        if (c->rec_gpl == 2)
-            build_records<2><<<layout_grid(c->rows * (Gp / 2)), 256, 0, c->stream>>>(c->d_source, c->d_sigT, c->d_records, c->rows, c->p.fine_axial_intervals, Gp);
-        else
-            build_records<4><<<layout_grid(c->rows * (Gp / 4)), 256, 0, c->stream>>>(c->d_source, c->d_sigT, c->d_records, c->rows, c->p.fine_axial_intervals, Gp);
+        // form 0: raw values; 1 / 2 (SMK_FLAG_FIT_PER_SWEEP): the fit evaluated here, once per (row, group), in the
+        // arithmetic of the kernel that reads it (per-lane-coefficient form for <= 32 groups, typed form for 33..64)
+        const int form = !c->hoist ? 0 : (Gp <= 32 ? 1 : 2);
+        const int F = c->p.fine_axial_intervals;
+#define SMK_BUILD(GPL, FORM) \
+    build_records<GPL, FORM><<<layout_grid(c->rows * (Gp / GPL)), 256, 0, c->stream>>>(c->d_source, c->d_sigT, c->d_records, c->rows, F, Gp)
+        if (c->rec_gpl == 2) {
+            if (form == 0) SMK_BUILD(2, 0); else if (form == 1) SMK_BUILD(2, 1); else SMK_BUILD(2, 2);
+        } else {
+            if (form == 0) SMK_BUILD(4, 0); else SMK_BUILD(4, 1);
+        }
+#undef SMK_BUILD
         SMK_CUDA(cudaGetLastError());
         c->launches += 1;
         lanes_per_track = Gp / c->rec_gpl;      // (32 for the one-track-per-warp shapes)

@@ -537,11 +537,14 @@ __device__ __forceinline__ Rec8 ldg256(const void *p)
     return r;
 }
 
-template <int GPL>
+// FORM 0: the raw values; FORM 1 / 2 (SMK_FLAG_FIT_PER_SWEEP): the fitted {q0, mu q1, mu2 q2} in the slots of
+// {y[FAI], y[FAI-1], y[FAI+1]}, evaluated by fit_row in the per-lane-coefficient form (1: attenuate_record_tracks) or the
+// statically typed form (2: attenuate_warp_track_rec) -- bit for bit what the sweep kernel would compute per segment.
+template <int GPL, int FORM>
 __global__ void build_records(const float *__restrict__ source, const float *__restrict__ sigT, float *__restrict__ rec,
                               int64_t rows, int fai_count, int groups_pad)
 {
-    // one thread per (row, GPL groups): writes 8 * GPL/2 floats... GPL = 2: one 32-byte record; GPL = 4: two
+    // one thread per (row, GPL groups): GPL = 2: one 32-byte record; GPL = 4: two
     const int per_row = groups_pad / GPL;
     const int64_t n = rows * per_row;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -559,6 +562,11 @@ __global__ void build_records(const float *__restrict__ source, const float *__r
             c[g] = yc[g];
             m[g] = fai > 0 ? yc[g - groups_pad] : 0.0f;
             p[g] = fai < fai_count - 1 ? yc[g + groups_pad] : 0.0f;
+            if constexpr (FORM != 0) {
+                float q0, Q1, Q2;
+                fit_row<FORM == 2>(fai == 0, fai == fai_count - 1, m[g], c[g], p[g], q0, Q1, Q2);
+                c[g] = q0; m[g] = Q1; p[g] = Q2;
+            }
         }
         if constexpr (GPL == 2) {
             out[0] = s[0]; out[1] = s[1]; out[2] = m[0]; out[3] = m[1];
@@ -583,45 +591,49 @@ constexpr int kRecordUnroll = SMK_REC_UNROLL;     // segment loop of attenuate_r
 // one segment of one lane of attenuate_record_tracks.  CHECK: the lane may be past its track's end (the stream's ragged
 // last track, or a warp slot without a track): it computes along with its warp-mates, tallies nothing, keeps its psi.
 // `fit` points at the coefficients of the segment: {q0_d, q0_s, q1_d, q1_s} {q2_s, ds, weight, -}
-template <int LPT, int GPL, int EXPM, bool F64, bool GEOM, bool CHECK>
+template <int LPT, int GPL, int EXPM, bool F64, bool GEOM, bool HOIST, bool CHECK>
 __device__ __forceinline__ void record_segment(const char *rec, const float4 *fit, const float2 *s_pairs, float *tally,
                                                double *tally64, uint32_t pidx, int sub, bool active,
                                                typename LaneVec<GPL>::type &psi)
 {
     typedef typename LaneVec<GPL>::type V;
-    const uint32_t idx = (pidx & ~(kRowFirst | kRowLast)) | (uint32_t)sub;
+    const uint32_t idx = (HOIST ? pidx : (pidx & ~(kRowFirst | kRowLast))) | (uint32_t)sub;
     const char *r = ptr_add_index<true>(rec, idx * (16u * GPL));
-    const float4 f0 = fit[0];
-    FitCoeffs fc;
-    fc.q0_d = f0.x; fc.q0_s = f0.y; fc.q1_d = f0.z; fc.q1_s = f0.w;
-    if constexpr (GEOM) {
-        const float4 f1 = fit[1];
-        fc.q2_s = f1.x; fc.ds = f1.y; fc.weight = f1.z;
-    } else {
-        fc.q2_s = *reinterpret_cast<const float *>(fit + 1);
-        fc.ds = Geometry::ds; fc.weight = Geometry::weight;
+    constexpr int kFit = HOIST ? kFitGiven : kFitDynamic;      // HOIST: the records hold the fitted coefficients
+    FitCoeffs fc = {};
+    if constexpr (!HOIST) {
+        const float4 f0 = fit[0];
+        fc.q0_d = f0.x; fc.q0_s = f0.y; fc.q1_d = f0.z; fc.q1_s = f0.w;
+        if constexpr (GEOM) {
+            const float4 f1 = fit[1];
+            fc.q2_s = f1.x; fc.ds = f1.y; fc.weight = f1.z;
+        } else {
+            fc.q2_s = *reinterpret_cast<const float *>(fit + 1);
+        }
     }
+    if constexpr (!GEOM) { fc.ds = Geometry::ds; fc.weight = Geometry::weight; }
     V t;
     if constexpr (GPL == 2) {
         const Rec8 q = ldg256(r);
         float2 ps = psi;
-        attenuate_fast2<EXPM, kFitDynamic, GEOM>(fc, q.b, q.c, q.d, q.a, s_pairs, ps, t);
+        attenuate_fast2<EXPM, kFit, GEOM>(fc, q.b, q.c, q.d, q.a, s_pairs, ps, t);
         if (!CHECK || active) psi = ps;                                       // kernel.c:331
     } else {
         const Rec8 q0 = ldg256(r), q1 = ldg256(r + 32);
         float2 p_lo = make_float2(psi.x, psi.y), p_hi = make_float2(psi.z, psi.w), t_lo, t_hi;
-        attenuate_fast2<EXPM, kFitDynamic, GEOM>(fc, q1.a, q0.c, q1.c, q0.a, s_pairs, p_lo, t_lo);
-        attenuate_fast2<EXPM, kFitDynamic, GEOM>(fc, q1.b, q0.d, q1.d, q0.b, s_pairs, p_hi, t_hi);
+        attenuate_fast2<EXPM, kFit, GEOM>(fc, q1.a, q0.c, q1.c, q0.a, s_pairs, p_lo, t_lo);
+        attenuate_fast2<EXPM, kFit, GEOM>(fc, q1.b, q0.d, q1.d, q0.b, s_pairs, p_hi, t_hi);
         if (!CHECK || active) psi = make_float4(p_lo.x, p_lo.y, p_hi.x, p_hi.y);
         t = make_float4(t_lo.x, t_lo.y, t_hi.x, t_hi.y);
     }
     if (!CHECK || active) tally_lane<F64, true>(tally, tally64, idx, t);      // kernel.c:276
 }
 
-template <int LPT, int GPL, int EXPM, bool F64, bool GEOM>
+template <int LPT, int GPL, int EXPM, bool F64, bool GEOM, bool HOIST = false>
 __global__ void __launch_bounds__(kThreadsPerBlock, kMinBlocksRec)
 attenuate_record_tracks(const KernelArgs a)
 {
+    static_assert(!(GEOM && HOIST), "the fit is only sweep-invariant with the constant geometry");
     static_assert(LPT >= 1 && LPT <= 16 && (LPT & (LPT - 1)) == 0, "LPT must be a power of two");
     static_assert(GPL == 2 || GPL == 4, "two or four groups per lane");
     typedef typename LaneVec<GPL>::type V;
@@ -636,7 +648,7 @@ attenuate_record_tracks(const KernelArgs a)
     // GEOM: per warp and hashing lane, the coefficients of that lane's segment of the batch (its type folded in),
     // {q0_d, q0_s, q1_d, q1_s} {q2_s, ds, weight, -}: derived once by the lane that hashed the segment.
     __shared__ float4 s_fit[GEOM ? kWarps * 64 : 8];
-    if constexpr (!GEOM) {
+    if constexpr (!GEOM && !HOIST) {
         if (threadIdx.x < 4) {
             const FitCoeffs f = fit_coeffs(threadIdx.x == 1, threadIdx.x == 2);
             s_fit[2 * threadIdx.x] = make_float4(f.q0_d, f.q0_s, f.q1_d, f.q1_s);
@@ -688,12 +700,14 @@ attenuate_record_tracks(const KernelArgs a)
             // each lane of the track draws the ids of one of the next LPT segments: idx = row * LPT (the lane's
             // element of the record row and of the tally row once `| sub` is added) + the two type flags.
             // Lanes without a segment keep row 0 with both flags: a valid address, nothing is tallied.
-            uint32_t my_idx = kRowFirst | kRowLast;
+            // (HOIST: the fitted records carry the segment type implicitly, no flags)
+            uint32_t my_idx = HOIST ? 0u : (kRowFirst | kRowLast);
             if (b + sub < nseg) {
                 const u32x4 w = stream_words(a.keys, seg, 0u, kDomainSegment);
                 const uint32_t qsr = fastmod(w.x >> 1, a.mod_regions);                   // kernel.c:47
                 const uint32_t fai = fastmod(w.y >> 1, a.mod_fai);                       // kernel.c:50
-                my_idx = ((qsr * F + fai) * (uint32_t)LPT) | (fai == 0u ? kRowFirst : 0u) | (fai == F - 1u ? kRowLast : 0u);
+                my_idx = (qsr * F + fai) * (uint32_t)LPT;
+                if constexpr (!HOIST) my_idx |= (fai == 0u ? kRowFirst : 0u) | (fai == F - 1u ? kRowLast : 0u);
                 checksum += checksum_term(qsr, fai, F, seg);
                 if constexpr (GEOM) {
                     const FitCoeffs f = fit_coeffs_geom(segment_geometry(a.geom, w.z, w.w), a.mesh, fai == 0u, fai == F - 1u);
@@ -710,13 +724,13 @@ attenuate_record_tracks(const KernelArgs a)
 #pragma unroll kRecordUnroll
                 for (int k = 0; k < count; ++k) {
                     const uint32_t pidx = __shfl_sync(kFull, my_idx, k, LPT);
-                    record_segment<LPT, GPL, EXPM, F64, GEOM, false>(rec, GEOM ? track_fit + 2 * k : s_fit + 2 * (pidx >> 30), s_pairs,
+                    record_segment<LPT, GPL, EXPM, F64, GEOM, HOIST, false>(rec, GEOM ? track_fit + 2 * k : s_fit + 2 * (pidx >> 30), s_pairs,
                                                                      tally, a.tally64, pidx, sub, true, psi);
                 }
             } else {
                 for (int k = 0; k < count; ++k) {
                     const uint32_t pidx = __shfl_sync(kFull, my_idx, k, LPT);
-                    record_segment<LPT, GPL, EXPM, F64, GEOM, true>(rec, GEOM ? track_fit + 2 * k : s_fit + 2 * (pidx >> 30), s_pairs,
+                    record_segment<LPT, GPL, EXPM, F64, GEOM, HOIST, true>(rec, GEOM ? track_fit + 2 * k : s_fit + 2 * (pidx >> 30), s_pairs,
                                                                     tally, a.tally64, pidx, sub, (b + k) < nseg, psi);
                 }
             }
@@ -743,10 +757,11 @@ attenuate_record_tracks(const KernelArgs a)
 // interleaving the sigT row with every source row (same loads off one address, one shuffle) is within the noise
 // (r02q): that shape is bound by the FP32 pipe, not by its 25 non-FP instructions per segment.
 // ------------------------------------------------------------------------------
-template <int EXPM, bool GEOM>
+template <int EXPM, bool GEOM, bool HOIST = false>
 __global__ void __launch_bounds__(kThreadsPerBlock, GEOM ? kMinBlocksGeom : kMinBlocksHalf)
 attenuate_warp_track_rec(const KernelArgs a)
 {
+    static_assert(!(GEOM && HOIST), "the fit is only sweep-invariant with the constant geometry");
     constexpr unsigned kFull = 0xFFFFFFFFu;
     constexpr int kWarps = kThreadsPerBlock / 32;
     constexpr uint32_t ROWV = 32;
@@ -810,7 +825,11 @@ attenuate_warp_track_rec(const KernelArgs a)
                     fc.q1_d = c1.x; fc.q1_s = c1.y; fc.q2_s = c1.z;
                 }
                 float2 t;
-                if ((int32_t)pk < 0) attenuate_lane<EXPM, kFitFirst, GEOM>(fc, q.b, q.c, q.d, q.a, s_pairs, psi, t);
+                if constexpr (HOIST) {
+                    // the records hold {q0, mu q1, mu2 q2}: one edge body (no quadratic terms) and the interior body
+                    if (pk & (kSgFirst | kSgLast)) attenuate_lane<EXPM, kFitGivenEdge, false>(fc, q.b, q.c, q.d, q.a, s_pairs, psi, t);
+                    else attenuate_lane<EXPM, kFitGiven, false>(fc, q.b, q.c, q.d, q.a, s_pairs, psi, t);
+                } else if ((int32_t)pk < 0) attenuate_lane<EXPM, kFitFirst, GEOM>(fc, q.b, q.c, q.d, q.a, s_pairs, psi, t);
                 else if (pk & kSgLast) attenuate_lane<EXPM, kFitLast, GEOM>(fc, q.b, q.c, q.d, q.a, s_pairs, psi, t);
                 else attenuate_lane<EXPM, kFitInterior, GEOM>(fc, q.b, q.c, q.d, q.a, s_pairs, psi, t);
                 tally_lane<false, true>(tally, nullptr, idx, t);                            // kernel.c:276

@@ -270,7 +270,9 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a
 // a - b with one rounding: fma(b, -1, a)
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, f2(-1.0f), a); }
 
-enum : int { kFitInterior = 0, kFitFirst = 1, kFitLast = 2, kFitDynamic = 3 };
+// kFitGiven / kFitGivenEdge: the fitted (q0, mu q1, mu2 q2) arrive in the (y2, y1, y3) arguments (SMK_FLAG_FIT_PER_SWEEP:
+// fit_row evaluated them once per (region, interval, group) of the sweep); the edge form skips the quadratic terms
+enum : int { kFitInterior = 0, kFitFirst = 1, kFitLast = 2, kFitDynamic = 3, kFitGiven = 4, kFitGivenEdge = 5 };
 
 // what finalize_flux multiplies the summed FAST tallies of the constant geometry by (see attenuate_fast2)
 constexpr float kTallyScaleConst = Geometry::weight;
@@ -323,6 +325,30 @@ __device__ __forceinline__ float2 exp_val2(float2 tau, const float2 *s_pairs, fl
     }
 }
 
+// The fit of attenuate_fast2 for ONE group, operation for operation (FFMA2 / FMUL2 / FADD2 are the scalar IEEE operations on
+// each half): TYPED = the statically typed bodies (kFitInterior / kFitFirst / kFitLast, constant geometry literals),
+// otherwise the per-lane-coefficient form (kFitDynamic with fit_coeffs(first, last), missing neighbour = 0).  Used by
+// build_records with SMK_FLAG_FIT_PER_SWEEP; the results are bit-identical to what the sweep kernels would compute.
+template <bool TYPED>
+__device__ __forceinline__ void fit_row(bool first, bool last, float y1, float y2, float y3, float &q0, float &Q1, float &Q2)
+{
+    using K = FitDiff;
+    if (TYPED && (first || last)) {
+        const float d = first ? __fmaf_rn(y2, -1.0f, y3) : __fmaf_rn(y1, -1.0f, y2);      // sub2(y3, y2) | sub2(y2, y1)
+        q0 = __fmaf_rn(K::e0, d, y2);
+        Q1 = __fmul_rn(K::e1, d);
+        Q2 = 0.0f;
+        return;
+    }
+    const FitCoeffs f = TYPED ? fit_coeffs(false, false) : fit_coeffs(first, last);
+    if (!TYPED) { y1 = first ? 0.0f : y1; y3 = last ? 0.0f : y3; }
+    const float d = __fmaf_rn(y3, -1.0f, y1);
+    const float s = __fmaf_rn(y2, -2.0f, __fadd_rn(y1, y3));
+    q0 = __fmaf_rn(f.q0_s, s, __fmaf_rn(f.q0_d, d, y2));
+    Q1 = __fmaf_rn(f.q1_s, s, __fmul_rn(f.q1_d, d));
+    Q2 = __fmul_rn(f.q2_s, s);
+}
+
 // Two intersections.  FIT selects the segment type at compile time (the edge types also skip the
 // quadratic terms, which are exactly zero there: q2 = 0, kernel.c:134,160) or, for kFitDynamic,
 // per-lane coefficients in the interior's form.  The coefficients are literals for the reference
@@ -332,11 +358,17 @@ __device__ __forceinline__ void attenuate_fast2(const FitCoeffs &f, float2 y1, f
                                                 float2 sigT, const float2 *s_pairs, float2 &psi,
                                                 float2 &tally)
 {
-    constexpr bool kQuadratic = (FIT == kFitInterior) || (FIT == kFitDynamic);
+    constexpr bool kGiven = (FIT == kFitGiven) || (FIT == kFitGivenEdge);
+    constexpr bool kQuadratic = (FIT == kFitInterior) || (FIT == kFitDynamic) || (FIT == kFitGiven);
     constexpr bool kFromF = GEOM || (FIT == kFitDynamic);
+    static_assert(!(kGiven && GEOM), "the fit is only sweep-invariant with the constant geometry");
     using K = FitDiff;
     float2 q0, Q1, Q2 = f2(0.0f);
-    if constexpr (kQuadratic) {
+    if constexpr (kGiven) {
+        q0 = y2;
+        Q1 = y1;
+        if constexpr (FIT == kFitGiven) Q2 = y3;
+    } else if constexpr (kQuadratic) {
         // d = y1 - y3, s = y1 - 2 y2 + y3:  c1 = d / (2 dz), c2 = s / (2 dz^2)   (kernel.c:182-184)
         const float2 d = sub2(y1, y3);
         const float2 s = fma2(y2, f2(-2.0f), add2(y1, y3));

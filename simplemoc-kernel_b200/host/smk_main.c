@@ -39,6 +39,7 @@ typedef struct {
     int host_fill;
     int tally_f64;
     int segment_geometry;      /* kernel.c:99-104 vary per segment (SMK_FLAG_SEGMENT_GEOMETRY) */
+    int fit_per_sweep;         /* source fit once per (region, interval, group) per sweep (SMK_FLAG_FIT_PER_SWEEP) */
     float geometry_spread;
     float sigt_floor;
     const char *dump_flux;
@@ -114,6 +115,8 @@ static void usage_and_exit(void)
     puts("  --host-fill           Fill the slabs on the host and upload them");
     puts("  --tally-f64           Diagnostic: accumulate the tallies in double precision");
     puts("  --segment-geometry    dz, zin, weight, mu, mu2, ds vary per segment (stream words 2,3)");
+    puts("  --fit-per-sweep       Evaluate the axial source fit once per (region, interval, group) per sweep,");
+    puts("                        not once per segment (same results; <= 64 groups; off by default)");
     puts("  --geometry-spread <x> Relative half-width of that variation, in [0, 1) (default 0.25)");
     puts("  --sigt-floor <x>      Well-conditioned diagnostic data: sigT in [x, 1)");
     puts("  --dump-flux <file>    Write the final scalar flux (raw float32)");
@@ -178,6 +181,7 @@ static void parse(int argc, char **argv, Input *I)
         else if (!strcmp(a, "--host-fill")) I->host_fill = 1;
         else if (!strcmp(a, "--tally-f64")) I->tally_f64 = 1;
         else if (!strcmp(a, "--segment-geometry")) I->segment_geometry = 1;
+        else if (!strcmp(a, "--fit-per-sweep")) I->fit_per_sweep = 1;
         else if (!strcmp(a, "--geometry-spread")) { I->geometry_spread = (float)atof(need(argc, argv, &i)); I->segment_geometry = 1; }
         else if (!strcmp(a, "--sigt-floor")) I->sigt_floor = (float)atof(need(argc, argv, &i));
         else if (!strcmp(a, "--dump-flux")) I->dump_flux = need(argc, argv, &i);
@@ -287,7 +291,8 @@ int main(int argc, char *argv[])
     p.exp_mode = I.exp_mode;
     p.math_mode = I.math_mode;
     p.device = I.device;
-    p.flags = (I.tally_f64 ? SMK_FLAG_TALLY_F64 : 0) | (I.segment_geometry ? SMK_FLAG_SEGMENT_GEOMETRY : 0);
+    p.flags = (I.tally_f64 ? SMK_FLAG_TALLY_F64 : 0) | (I.segment_geometry ? SMK_FLAG_SEGMENT_GEOMETRY : 0) |
+              (I.fit_per_sweep ? SMK_FLAG_FIT_PER_SWEEP : 0);
 
     smk_ctx *ctx = NULL;
     smk_multi *multi = NULL;

@@ -648,6 +648,53 @@ def test_warp_track_record_kernel_per_segment_geometry(smk, oracle, monkeypatch,
     assert np.array_equal(bits(out["0"][1]), bits(out["1"][1]))
 
 
+@pytest.mark.parametrize("R,F,G,N,p", [(70, 5, 7, 50_000, 100), (70, 5, 29, 20_003, 37), (70, 5, 3, 20_000, 10),
+                                       (70, 5, 13, 20_000, 100), (60, 5, 64, 40_033, 70), (60, 5, 40, 30_000, 100),
+                                       (40, 2, 7, 20_000, 100), (40, 2, 50, 20_000, 100), (14, 5, 64, 100_000, 100)])
+def test_fit_per_sweep_is_bit_identical(smk, oracle, R, F, G, N, p):
+    """SMK_FLAG_FIT_PER_SWEEP (off by default): the quadratic axial source fit (kernel.c:111-191) evaluated once per
+    (region, interval, group) per sweep by the record-layout pass instead of once per segment, same operations in
+    the same order.  psi per track and -- with the order-independent f64 tallies -- the flux must be bit-identical
+    to the per-segment evaluation; edge-only intervals (F = 2), ragged tracks, tally replicas (14 regions)."""
+    seed = 95
+    src, flux0, sig = oracle.fill(R, F, G, seed)
+    want = flux0.copy()
+    _, chk_want = oracle.run(src, want, sig, N, p, seed, nthreads=0)
+    out = {}
+    for hoist in (False, True):
+        for f64 in (True, False):
+            I = make_input(smk, R, F, G, N, p, seed, "poly", "fast", tally_f64=f64)
+            I.fit_per_sweep = hoist
+            with smk.Context(I, keep_psi=True) as ctx:
+                ctx.upload(src, flux0, sig)
+                name = ctx.kernel_name
+                ctx.run()
+                out[hoist, f64] = (ctx.download_flux(), ctx.download_psi(ctx.n_tracks), ctx.checksum())
+            # 33..64 groups: the f64-tally diagnostic keeps the row-array kernel, where the flag has no effect
+            assert ("fit per sweep" in name) == (hoist and (G <= 32 or not f64)), name
+            assert out[hoist, f64][2] == chk_want
+    assert np.array_equal(bits(out[True, False][1]), bits(out[False, False][1]))
+    assert np.array_equal(bits(out[True, True][1]), bits(out[False, True][1]))
+    assert np.array_equal(bits(out[True, True][0]), bits(out[False, True][0]))
+    if R > 14:                    # (14 regions = the few-row stress shape: fp32 accumulation order alone exceeds the gate)
+        assert l2rel(out[True, False][0], want) <= TOL_FAST
+
+
+def test_fit_per_sweep_needs_fast_math_and_constant_geometry(smk):
+    I = make_input(smk, 20, 5, 7, 1000, 100, 1, "glibc", "strict")
+    I.fit_per_sweep = True
+    with pytest.raises(smk.SmkError):
+        smk.Context(I)
+    I = make_input(smk, 20, 5, 7, 1000, 100, 1, "poly", "fast", geom=(REFERENCE_GEOMETRY, 0.25))
+    I.fit_per_sweep = True
+    with pytest.raises(smk.SmkError):
+        smk.Context(I)
+    I = make_input(smk, 20, 5, 128, 1000, 100, 1, "poly", "fast")      # accepted, no effect above 64 groups
+    I.fit_per_sweep = True
+    with smk.Context(I) as ctx:
+        assert "fit per sweep" not in ctx.kernel_name
+
+
 @pytest.mark.parametrize("exp_mode", ["mufu", "glibc", "table"])
 def test_record_kernel_other_exponentials_and_f64_tallies(smk, oracle, monkeypatch, exp_mode):
     """Every exponential of the record kernel against the general kernel: psi bit-identical, and with the f64 tally
