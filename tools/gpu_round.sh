@@ -18,7 +18,7 @@ done
 echo "== expf sweep"; timeout 900 python tools/expf_sweep.py > $OUT/expf_sweep_$TAG.md 2>&1; tail -6 $OUT/expf_sweep_$TAG.md
 echo "== compute-sanitizer"
 ( for tool in memcheck racecheck synccheck; do
-    echo "== $tool"; timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "golden or record or (geometry_strict and 200-5-128)" 2>&1 | tail -4
+    echo "== $tool"; timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "golden or record or fit_per_sweep or pipelined or (geometry_strict and 200-5-128)" 2>&1 | tail -4
   done ) > $OUT/sanitizer_$TAG.log 2>&1; grep -E "SUMMARY|passed|failed" $OUT/sanitizer_$TAG.log
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/launches_$TAG.csv \
