@@ -236,11 +236,11 @@ def lane_ops_per_intersection(smk, egroups, F, geometry, fit_per_sweep=False):
     intersection where the segment type is warp-uniform (33..128 groups: one track per warp), 45 for every
     intersection where tracks of different types share a warp (<= 32 groups) or rows are swept in blocks;
     one more with per-segment geometry (the weight is applied per intersection instead of once at the end).
-    With --fit-per-sweep (SMK_FLAG_FIT_PER_SWEEP, <= 64 groups) the fit's 8 (interior) / 3 (edge) operations are
+    With --fit-per-sweep (SMK_FLAG_FIT_PER_SWEEP, <= 128 groups) the fit's 8 (interior) / 3 (edge) operations are
     evaluated per (region, interval, group) and sweep instead: 37 / 26 remain in the segment loop."""
     extra = 1.0 if geometry else 0.0
     gp = smk.lib.smk_padded_groups(egroups)
-    hoist = fit_per_sweep and gp <= 64 and not geometry
+    hoist = fit_per_sweep and gp <= 128 and not geometry
     interior, edge = (37.0, 26.0) if hoist else (45.0, 29.0)
     if gp >= 64:
         return ((interior + extra) * (F - 2) + (edge + extra) * 2) / F
@@ -372,7 +372,7 @@ def e2e_run(torch, dist, smk, dev, rank, world, a, steps):
     segments = 100_000_000 * world if a.segments == CONFIG5_SEGMENTS else a.segments   # config 2 (per GPU)
     I = smk.Input(source_2D_regions=a.regions_2d, segments=segments, egroups=G, seg_per_thread=a.seg_per_track,
                   seed=a.seed, exp_mode=a.exp, math_mode=a.math, device=dev.index,
-                  segment_geometry=a.geometry).finalize()
+                  segment_geometry=a.geometry, fit_per_sweep=a.fit_per_sweep).finalize()
     R, F = I.source_3D_regions, I.fine_axial_intervals
     rows = R * F
     tb, te = multi.shard_tracks(I.n_tracks, rank, world)
@@ -569,6 +569,7 @@ def main_ours(a):
                          ("hbm_resident_432000_regions", dict(regions_2d=320000, hbm_resident=True)),
                          ("config2_per_segment_geometry", dict(geometry=True)),
                          # NOT the default arithmetic: the source fit hoisted out of the segment loop (same results)
+                         ("config2_fit_per_sweep", dict(fit_per_sweep=True)),
                          ("config3_7_groups_fit_per_sweep", dict(egroups=7, fit_per_sweep=True)),
                          ("config4_64_groups_14_regions_fit_per_sweep", dict(egroups=64, regions_2d=10, fit_per_sweep=True)),
                          ("config5_1e10_segments_one_gpu", dict(segments=CONFIG5_SEGMENTS, steps=1, warmup=1))):

@@ -93,8 +93,8 @@ typedef struct smk_params {
                                        are bit-identical, 8 of 45 operations per interior intersection leave the segment
                                        loop.  The reference evaluates the fit per segment, so the default does too;
                                        needs SMK_MATH_FAST and the constant geometry (SMK_EINVAL otherwise), and takes
-                                       effect for the shapes that sweep from gather records (<= 64 groups, working set
-                                       within the L2) -- smk_kernel_name says which form runs. */
+                                       effect up to 128 groups while the derived arrays fit the L2 (f32 tallies) --
+                                       smk_kernel_name says which form runs. */
 
 /*
  * Segment geometry.  /root/reference/src/cpu/kernel.c:95-104: "Some placeholder constants - In the

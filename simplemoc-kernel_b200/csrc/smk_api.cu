@@ -208,6 +208,16 @@ static AttenuateFn pick_record_hoist(int groups_pad, int gpl, int expm, bool f64
     return nullptr;
 }
 
+static AttenuateFn pick_warp_track_fit(int expm)
+{
+    switch (expm) {
+        case kExpPoly: return attenuate_warp_track_fit<kExpPoly>;
+        case kExpPolyWide: return attenuate_warp_track_fit<kExpPolyWide>;
+        case kExpMufu: return attenuate_warp_track_fit<kExpMufu>;
+    }
+    return nullptr;
+}
+
 static AttenuateFn pick_warp_track_rec_hoist(int expm)
 {
     switch (expm) {
@@ -414,6 +424,11 @@ static int select_kernel(smk_ctx *c)
         c->hoist = fn != nullptr;
         if (!fn) fn = pick_record(c->shape.groups_pad, c->rec_gpl, expm, f64, geom);
         family = c->rec_gpl == 2 ? "attenuate_record_tracks<2 groups/lane" : "attenuate_record_tracks<4 groups/lane";
+    } else if (!fn && c->d_records && c->shape.groups_pad == 128) {
+        // (allocated only with SMK_FLAG_FIT_PER_SWEEP: the fitted rows of attenuate_warp_track_fit)
+        fn = pick_warp_track_fit(expm);
+        c->hoist = fn != nullptr;
+        family = "attenuate_warp_track_fit<4 groups/lane";
     } else if (!fn && c->d_records) {
         if (want_hoist) fn = pick_warp_track_rec_hoist(expm);
         c->hoist = fn != nullptr;
@@ -573,6 +588,15 @@ int smk_create(const smk_params *p, smk_ctx **out)
         if (wt_eligible && !plain64 && !(wt && wt[0] == '0')) {
             c->rec_gpl = 2;
             if (e == cudaSuccess) e = cudaMalloc(&c->d_records, slab * 4);
+        }
+        // 65..128 groups with SMK_FLAG_FIT_PER_SWEEP: three fitted rows per source row (attenuate_warp_track_fit), while
+        // they and the tallies fit in 3/4 of the L2
+        const bool fit_eligible = (p->flags & SMK_FLAG_FIT_PER_SWEEP) && shape.nchunk == 1 && shape.lpt == 32 &&
+                                  !(p->flags & SMK_FLAG_TALLY_F64) && slab * 3 < (1ull << 32) && !plain64 &&
+                                  e == cudaSuccess && (double)slab * 4.25 <= 0.75 * (double)prop.l2CacheSize;
+        if (fit_eligible) {
+            c->rec_gpl = 4;
+            e = cudaMalloc(&c->d_records, slab * 3);
         }
     }
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tally, 0, slab * c->replicas, c->stream);
@@ -862,7 +886,9 @@ static int launch(smk_ctx *c, int64_t track_begin, int64_t track_end)
         const int F = c->p.fine_axial_intervals;
 #define SMK_BUILD(GPL, FORM) \
     build_records<GPL, FORM><<<layout_grid(c->rows * (Gp / GPL)), 256, 0, c->stream>>>(c->d_source, c->d_sigT, c->d_records, c->rows, F, Gp)
-        if (c->rec_gpl == 2) {
+        if (Gp == 128) {      // 65..128 groups (SMK_FLAG_FIT_PER_SWEEP only): three fitted rows per source row
+            build_fit_rows<<<layout_grid(c->rows * Gp), 256, 0, c->stream>>>(c->d_source, c->d_records, c->rows, F, Gp);
+        } else if (c->rec_gpl == 2) {
             if (form == 0) SMK_BUILD(2, 0); else if (form == 1) SMK_BUILD(2, 1); else SMK_BUILD(2, 2);
         } else {
             if (form == 0) SMK_BUILD(4, 0); else SMK_BUILD(4, 1);

@@ -847,6 +847,107 @@ attenuate_warp_track_rec(const KernelArgs a)
 }
 
 // ------------------------------------------------------------------------------
+// SMK_FLAG_FIT_PER_SWEEP at 65..128 groups: build_fit_rows evaluates the typed fit once per (region, interval, group)
+// of the sweep into fit[row][{q0, mu q1, mu2 q2}][G_pad] (three rows of 128 groups side by side, so the loads of a
+// segment hang off one address with immediate offsets), and attenuate_warp_track_fit<EXPM> is attenuate_warp_track<4>
+// reading them: 37 / 26 operations per interior / edge intersection instead of 45 / 29, the same 3-4 loads of 128 bits
+// per lane and segment (an edge interval has no q2), psi bit-identical.  f32 tallies, constant geometry, 32-bit offsets.
+// ------------------------------------------------------------------------------
+__global__ void build_fit_rows(const float *__restrict__ source, float *__restrict__ fit, int64_t rows, int fai_count,
+                               int groups_pad)
+{
+    const int64_t n = rows * groups_pad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / groups_pad;
+        const int g = (int)(i - row * groups_pad);
+        const int fai = (int)(row % fai_count);
+        const float y2 = source[i];
+        const float y1 = fai > 0 ? source[i - groups_pad] : 0.0f;
+        const float y3 = fai < fai_count - 1 ? source[i + groups_pad] : 0.0f;
+        float q0, Q1, Q2;
+        fit_row<true>(fai == 0, fai == fai_count - 1, y1, y2, y3, q0, Q1, Q2);
+        float *out = fit + row * 3 * groups_pad + g;
+        out[0] = q0;
+        out[groups_pad] = Q1;
+        out[2 * groups_pad] = Q2;
+    }
+}
+
+template <int EXPM>
+__global__ void __launch_bounds__(kThreadsPerBlock, kMinBlocksFast)
+attenuate_warp_track_fit(const KernelArgs a)
+{
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    constexpr int kWarps = kThreadsPerBlock / 32;
+    constexpr uint32_t ROWV = 32;
+
+    __shared__ float2 s_pairs[kTableReach];
+    if constexpr (EXPM == kExpTable) {
+        if (threadIdx.x < kTableReach) s_pairs[threadIdx.x] = c_exp_table.pairs[threadIdx.x];
+        __syncthreads();
+    }
+    int lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const int warp = threadIdx.x >> 5;
+    const int64_t warp_global = (int64_t)blockIdx.x * kWarps + warp;
+    const uint32_t F = (uint32_t)a.fai_count;
+    const int p = a.seg_per_track;
+    const float4 *const fit = reinterpret_cast<const float4 *>(a.records);
+    float *const tally = warp_tally(a, warp_global);
+    const int64_t n_tracks = a.track_end - a.track_begin;
+    unsigned long long checksum = 0ull;
+    const FitCoeffs fc = {};
+
+    for (int64_t w = claim_work(a, lane, 1); w < n_tracks; w = claim_work(a, lane, 1)) {
+        const int64_t track = a.track_begin + w;
+        const int64_t s0 = track * p;
+        const int64_t left = a.segments - s0;
+        const int nseg = left < p ? (int)left : p;
+        const u32x4 r0 = stream_words(a.keys, (uint64_t)track, (uint32_t)lane, kDomainPsi);
+        float4 psi = make_float4(u01(r0.x), u01(r0.y), u01(r0.z), u01(r0.w));
+
+        for (int b = 0; b < nseg; b += 32) {
+            uint32_t my_pk = 0u, my_sg = 0u;
+            if (b + lane < nseg) {
+                const uint64_t seg = (uint64_t)(s0 + b + lane);
+                const u32x4 r = stream_words(a.keys, seg, 0u, kDomainSegment);
+                const uint32_t qsr = fastmod(r.x >> 1, a.mod_regions);       // kernel.c:47
+                const uint32_t fai = fastmod(r.y >> 1, a.mod_fai);           // kernel.c:50
+                checksum += checksum_term(qsr, fai, F, seg);
+                my_pk = (qsr * F + fai) * ROWV;
+                my_sg = (qsr * ROWV) | ((fai == 0u || fai == F - 1u) ? kSgFirst : 0u);      // one flag: edge interval
+            }
+            const int count = (nseg - b) < 32 ? (nseg - b) : 32;
+#pragma unroll kSegmentUnroll
+            for (int k = 0; k < count; ++k) {
+                const uint32_t pk = __shfl_sync(kFull, my_pk, k);
+                const uint32_t idx = pk | (uint32_t)lane;
+                const uint32_t sg = __shfl_sync(kFull, my_sg, k);
+                // row * 96 lane vectors: the fitted rows of `row`
+                const float4 *src = ptr_add_index<true>(fit, (pk + (pk << 1)) | (uint32_t)lane);
+                const float4 st = ldg4(ptr_add_index<true>(a.sigT, (sg & ~kSgFirst) | (uint32_t)lane));
+                const float4 q0 = ldg4(src), Q1 = ldg4(src + ROWV);
+                float4 t;
+                if ((int32_t)sg < 0) {
+                    attenuate_lane<EXPM, kFitGivenEdge, false>(fc, Q1, q0, make_float4(0.f, 0.f, 0.f, 0.f), st, s_pairs, psi, t);
+                } else {
+                    const float4 Q2 = ldg4(src + 2 * ROWV);
+                    attenuate_lane<EXPM, kFitGiven, false>(fc, Q1, q0, Q2, st, s_pairs, psi, t);
+                }
+                tally_lane<false, true>(tally, nullptr, idx, t);                            // kernel.c:276
+            }
+        }
+
+        if (a.psi_out != nullptr)
+            reinterpret_cast<float4 *>(a.psi_out)[(track - a.track_begin) * ROWV + lane] = psi;
+    }
+
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) checksum += __shfl_xor_sync(kFull, checksum, off);
+    if (lane == 0 && checksum != 0ull) atomicAdd(a.checksum, checksum);
+}
+
+// ------------------------------------------------------------------------------
 // layout kernels
 // ------------------------------------------------------------------------------
 

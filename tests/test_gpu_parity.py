@@ -650,7 +650,8 @@ def test_warp_track_record_kernel_per_segment_geometry(smk, oracle, monkeypatch,
 
 @pytest.mark.parametrize("R,F,G,N,p", [(70, 5, 7, 50_000, 100), (70, 5, 29, 20_003, 37), (70, 5, 3, 20_000, 10),
                                        (70, 5, 13, 20_000, 100), (60, 5, 64, 40_033, 70), (60, 5, 40, 30_000, 100),
-                                       (40, 2, 7, 20_000, 100), (40, 2, 50, 20_000, 100), (14, 5, 64, 100_000, 100)])
+                                       (40, 2, 7, 20_000, 100), (40, 2, 50, 20_000, 100), (14, 5, 64, 100_000, 100),
+                                       (60, 5, 128, 30_011, 100), (40, 2, 100, 20_000, 1000)])
 def test_fit_per_sweep_is_bit_identical(smk, oracle, R, F, G, N, p):
     """SMK_FLAG_FIT_PER_SWEEP (off by default): the quadratic axial source fit (kernel.c:111-191) evaluated once per
     (region, interval, group) per sweep by the record-layout pass instead of once per segment, same operations in
@@ -670,7 +671,7 @@ def test_fit_per_sweep_is_bit_identical(smk, oracle, R, F, G, N, p):
                 name = ctx.kernel_name
                 ctx.run()
                 out[hoist, f64] = (ctx.download_flux(), ctx.download_psi(ctx.n_tracks), ctx.checksum())
-            # 33..64 groups: the f64-tally diagnostic keeps the row-array kernel, where the flag has no effect
+            # 33..128 groups: the f64-tally diagnostic keeps the row-array kernel, where the flag has no effect
             assert ("fit per sweep" in name) == (hoist and (G <= 32 or not f64)), name
             assert out[hoist, f64][2] == chk_want
     assert np.array_equal(bits(out[True, False][1]), bits(out[False, False][1]))
@@ -689,7 +690,7 @@ def test_fit_per_sweep_needs_fast_math_and_constant_geometry(smk):
     I.fit_per_sweep = True
     with pytest.raises(smk.SmkError):
         smk.Context(I)
-    I = make_input(smk, 20, 5, 128, 1000, 100, 1, "poly", "fast")      # accepted, no effect above 64 groups
+    I = make_input(smk, 20, 5, 200, 1000, 100, 1, "poly", "fast")      # accepted, no effect above 128 groups
     I.fit_per_sweep = True
     with smk.Context(I) as ctx:
         assert "fit per sweep" not in ctx.kernel_name
