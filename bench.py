@@ -564,14 +564,16 @@ def main_ours(a):
     # ---- extra legs / sub-records ---------------------------------------------------------------
     legs, weak, single = [], None, None
     if not a.no_legs and world == 1:
+        # (each opt-in fit-per-sweep leg right after its default-arithmetic twin: the board sits on its power cap and the
+        # clock sags over a run, so distant legs are not comparable)
         for name, kw in (("config3_7_groups", dict(egroups=7)),
+                         # NOT the default arithmetic: the source fit hoisted out of the segment loop (same results)
+                         ("config3_7_groups_fit_per_sweep", dict(egroups=7, fit_per_sweep=True)),
                          ("config4_64_groups_14_regions", dict(egroups=64, regions_2d=10)),
+                         ("config4_64_groups_14_regions_fit_per_sweep", dict(egroups=64, regions_2d=10, fit_per_sweep=True)),
+                         ("config2_fit_per_sweep", dict(fit_per_sweep=True)),
                          ("hbm_resident_432000_regions", dict(regions_2d=320000, hbm_resident=True)),
                          ("config2_per_segment_geometry", dict(geometry=True)),
-                         # NOT the default arithmetic: the source fit hoisted out of the segment loop (same results)
-                         ("config2_fit_per_sweep", dict(fit_per_sweep=True)),
-                         ("config3_7_groups_fit_per_sweep", dict(egroups=7, fit_per_sweep=True)),
-                         ("config4_64_groups_14_regions_fit_per_sweep", dict(egroups=64, regions_2d=10, fit_per_sweep=True)),
                          ("config5_1e10_segments_one_gpu", dict(segments=CONFIG5_SEGMENTS, steps=1, warmup=1))):
             legs.append(run_leg(torch, dist, smk, dev, rank, world, flush, a, name, **kw))
     nccl_flux = None
